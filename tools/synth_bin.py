@@ -56,7 +56,7 @@ def _transpose_perm(in_dims, out_dims):
     raise ValueError('cannot derive Transpose permutation {} -> {}'.format(in_dims, out_dims))
 
 
-def synth_blob(xml_path, seed=0, cls_bias=-4.0):
+def synth_blob(xml_path, seed=0, cls_bias=-2.2):
     """Return the bytes of a synthetic `.bin` for `xml_path`."""
     layers, edges = _parse(xml_path)
     consumers = {}
