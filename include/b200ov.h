@@ -1,0 +1,183 @@
+/*
+ * b200ov.h -- C ABI of libb200ov.so: the B200 (sm_100a) kernels behind pyOpenVINO's op-plugin
+ * compute() contract.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / POD descriptors and a
+ * cudaStream_t passed as `void*`; no C++ or torch types cross this boundary.  All functions
+ * return B200OV_OK (0) or an error code; b200ov_last_error() returns the message of the last
+ * failure on the calling thread.  Nothing here falls back to the CPU.
+ *
+ * Device tensor conventions
+ *   - activations: float32, physical layout NHWC with a channel pitch `ld` (floats between
+ *     consecutive pixels, ld >= C).  ld > C lets a producer write straight into a channel slice
+ *     of a Concat buffer.  The logical (IR) shape stays NCHW; the Python host tracks the tag.
+ *   - 2-D tensors (MatMul operands, SoftMax rows): row-major.
+ *   - conv weights: packed once per network by b200ov_pack_conv_weights() to
+ *     [K = kh*kw*cin rows (padded to a multiple of 16)][ldw = cout padded to a multiple of 64].
+ *
+ * Each function cites the reference interface it replaces (paths relative to the
+ * yas-sim/pyopenvino root).
+ */
+#ifndef B200OV_H
+#define B200OV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200OV_VERSION 100
+
+enum {
+  B200OV_OK = 0,
+  B200OV_ERR_INVALID = 1,     /* bad descriptor / argument */
+  B200OV_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed */
+  B200OV_ERR_UNSUPPORTED = 3  /* valid request this build has no kernel for */
+};
+
+/* fused activation applied last in every epilogue */
+enum {
+  B200OV_ACT_NONE = 0,
+  B200OV_ACT_RELU = 1,    /* ReLU.py:9-12   : x < 0 ? 0 : x            */
+  B200OV_ACT_CLAMP = 2,   /* Clamp.py:9-12  : min(max(x, lo), hi)      */
+  B200OV_ACT_SIGMOID = 3  /* Sigmoid.py:10-13: 1 / (1 + exp(-x))       */
+};
+
+/* arithmetic used by the dense contractions */
+enum {
+  B200OV_MATH_AUTO = 0,     /* pick per shape: tcgen05 3xTF32 when eligible, else FP32 FFMA */
+  B200OV_MATH_FP32 = 1,     /* CUDA-core FP32 FFMA implicit GEMM                                */
+  B200OV_MATH_TF32X3 = 2,   /* tcgen05 kind::tf32, hi/lo split, 3 MMAs, FP32 accumulate in TMEM */
+  B200OV_MATH_TF32 = 3      /* tcgen05 kind::tf32 single pass (1e-3 tolerance class)            */
+};
+
+/* ---- library / device -------------------------------------------------------------------- */
+int b200ov_version(void);
+const char* b200ov_last_error(void);
+/* Select the device for the calling thread and cache its properties. */
+int b200ov_init(int device);
+int b200ov_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem_bytes);
+
+/* ---- memory, copies, streams (the Python host usually brings torch-owned pointers instead) -- */
+int b200ov_malloc(void** dptr, size_t bytes);
+int b200ov_free(void* dptr);
+int b200ov_host_alloc(void** hptr, size_t bytes);   /* pinned */
+int b200ov_host_free(void* hptr);
+int b200ov_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int b200ov_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int b200ov_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int b200ov_memset(void* dst, int value, size_t bytes, void* stream);
+int b200ov_stream_create(void** stream);
+int b200ov_stream_destroy(void* stream);
+int b200ov_stream_sync(void* stream);
+
+/* CUDA-graph capture of a launch sequence (replaces the per-node python dispatch loop of
+ * Executable_Network.run_tasks, inference_engine.py:259-292, on the replay path). */
+int b200ov_graph_begin(void* stream);
+int b200ov_graph_end(void* stream, void** graph_exec);
+int b200ov_graph_launch(void* graph_exec, void* stream);
+int b200ov_graph_destroy(void* graph_exec);
+
+/* ---- Convolution / MatMul ------------------------------------------------------------------ */
+typedef struct {
+  int32_t n, h, w, cin;        /* input  [n][h][w][cin], pixel pitch x_ld                        */
+  int32_t cout, kh, kw;        /* filter                                                         */
+  int32_t sh, sw;              /* strides                                                        */
+  int32_t pt, pl;              /* pads_begin (top, left); zero padding, Convolution.py:63,104    */
+  int32_t oh, ow;              /* output size from calc_output_shape, Convolution.py:21-49       */
+  int32_t x_ld, y_ld;          /* channel pitch of input / output pixels (floats)                */
+  int32_t ldw;                 /* pitch of the packed weight rows (floats)                       */
+  int32_t act;                 /* B200OV_ACT_*                                                   */
+  float act_lo, act_hi;        /* Clamp bounds                                                   */
+  int32_t math;                /* B200OV_MATH_*                                                  */
+} b200ov_conv_desc;
+
+/* OIHW -> packed [kh*kw*cin (pad 16)][ldw] (row index ordered ky, kx, ci).  `ldw` and the row
+ * count come from b200ov_conv_weight_dims().  Replaces `kernel.reshape(kn,-1).T`, Convolution.py:83. */
+int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* ldw);
+int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int cin, int kh, int kw, void* stream);
+
+/* y = act(conv(x, w) + bias).  Replaces Convolution.compute (Convolution.py:149-176) and, through
+ * the epilogue, the Add (Add.py:9-14) and ReLU / Clamp nodes that follow it.  `bias` may be NULL. */
+int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias,
+                  float* y, void* stream);
+
+/* Y[m][n] = act(sum_k A[m][k] * Bkn[k][n] + bias[n]); Bkn is the packed form of a 1x1 conv weight
+ * (b200ov_pack_conv_weights with kh = kw = 1 on B[n][k]).  Replaces MatMul.compute for
+ * transpose_a=false / transpose_b=true (MatMul.py:9-17); other flag combinations are brought to
+ * this form by the host with b200ov_transpose. */
+int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw,
+                  const float* bias, int act, float act_lo, float act_hi, int math,
+                  float* y, int ldy, void* stream);
+
+/* ---- depthwise GroupConvolution ------------------------------------------------------------ */
+typedef struct {
+  int32_t n, h, w, c;
+  int32_t kh, kw, sh, sw, pt, pl, oh, ow;
+  int32_t x_ld, y_ld;
+  int32_t act;
+  float act_lo, act_hi;
+} b200ov_dwconv_desc;
+
+/* [C][1][1][kh][kw] -> [kh*kw][C] */
+int b200ov_pack_dw_weights(const float* w_g11hw, float* w_packed, int c, int kh, int kw, void* stream);
+/* Replaces GroupConvolution.compute (GroupConvolution.py:114-137, depthwise case) + Add + Clamp.
+ * Products are summed in numpy's pairwise order without FMA contraction, so the pre-bias value is
+ * bit-identical to `np.sum(patch*flt)` (GroupConvolution.py:78). */
+int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_packed, const float* bias,
+                    float* y, void* stream);
+
+/* ---- pooling --------------------------------------------------------------------------------- */
+enum { B200OV_POOL_MAX = 0, B200OV_POOL_AVG_REF = 1 };
+typedef struct {
+  int32_t n, h, w, c;
+  int32_t kh, kw, sh, sw;
+  int32_t pt, pl, pb, pr;      /* pads_begin / pads_end                                          */
+  int32_t oh, ow;
+  int32_t x_ld, y_ld;
+  int32_t mode;                /* MAX: zero padding takes part, overhang clipped (MaxPool.py:53,69)
+                                  AVG_REF: no padding, window clipped at h-1 / w-1 (AvgPool.py:56) */
+} b200ov_pool_desc;
+/* Replaces MaxPool.compute (MaxPool.py:111-135) / AvgPool.compute (AvgPool.py:94-118).  Optional
+ * per-channel epilogue y = y*scale[c] + shift[c] (the folded BatchNorm Multiply+Add that follows
+ * the pools of mnist_bn); either pointer may be NULL. */
+int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const float* scale, const float* shift,
+                  float* y, void* stream);
+
+/* ---- elementwise tail -------------------------------------------------------------------------- */
+/* y[i] = act((x[i] * s) + b) over rows x C elements with channel = i % C (NHWC pixels or 2-D rows).
+ *   scale_vec / shift_vec : per-channel vectors or NULL; when NULL the scalar scale_s / shift_s is
+ *   used, and has_scale / has_shift == 0 skips the step entirely (keeps results bit-identical to
+ *   the separate numpy ops).  Replaces Add.py:9-14, Multiply.py:9-17 (broadcast operand cases),
+ *   ReLU.py:9-12, Clamp.py:9-12, Sigmoid.py:10-13 as standalone nodes. */
+int b200ov_affine_act(const float* x, float* y, int64_t rows, int c, int x_ld, int y_ld,
+                      int has_scale, const float* scale_vec, float scale_s,
+                      int has_shift, const float* shift_vec, float shift_s,
+                      int act, float act_lo, float act_hi, void* stream);
+/* y = a (+|*) b for two tensors of identical shape; op 0 = add, 1 = multiply. */
+int b200ov_binary(int op, const float* a, const float* b, float* y, int64_t count, void* stream);
+/* Row softmax, y[r][:] = exp(x[r][:]) / sum(exp(x[r][:])) (max-shifted form).  Replaces
+ * SoftMax.compute (SoftMax.py:10-14); batched meaning = one row per image. */
+int b200ov_softmax(const float* x, float* y, int rows, int cols, void* stream);
+/* Across-channel LRN on NHWC pixels, LRN.py:10-22 (alpha NOT divided by size). */
+int b200ov_lrn(const float* x, float* y, int64_t pixels, int c, int x_ld, int y_ld, int size,
+               float alpha, float beta, float bias, void* stream);
+
+/* ---- layout glue ----------------------------------------------------------------------------- */
+/* [batch][rows][cols] -> [batch][cols][rows] with an output pitch (NCHW<->NHWC, Transpose.py:9-13,
+ * MatMul transpose flags).  Optional y = x*scale[c]+shift[c] on the fly when the source is NCHW
+ * (c = row index): the Parameter -> mean/scale pre-processing of GoogLeNet / SSD. */
+int b200ov_transpose(const float* x, float* y, int batch, int rows, int cols, int x_ld, int y_ld,
+                     void* stream);
+int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, int y_ld,
+                               int has_scale, const float* scale_vec, float scale_s,
+                               int has_shift, const float* shift_vec, float shift_s, void* stream);
+/* rows x cols strided copy (Concat.py:9-13 when producers could not write in place). */
+int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OV_H */

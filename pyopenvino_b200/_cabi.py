@@ -1,0 +1,117 @@
+"""ctypes binding of libb200ov.so (the C ABI declared in include/b200ov.h).
+
+There is no CPU fallback: importing this module without the built library, or calling a kernel
+without a CUDA device, raises.  Build with `python -m pyopenvino_b200.build`.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libb200ov.so')
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_CLAMP, ACT_SIGMOID = 0, 1, 2, 3
+MATH_AUTO, MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2, 3
+POOL_MAX, POOL_AVG_REF = 0, 1
+
+
+class B200ovError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'cin', 'cout', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
+                                         'x_ld', 'y_ld', 'ldw', 'act')] + \
+               [('act_lo', C.c_float), ('act_hi', C.c_float), ('math', C.c_int32)]
+
+
+class DwConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
+                                         'x_ld', 'y_ld', 'act')] + [('act_lo', C.c_float), ('act_hi', C.c_float)]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'pb', 'pr', 'oh', 'ow',
+                                         'x_ld', 'y_ld', 'mode')]
+
+
+_P, _I, _F, _L, _Z = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+
+# name -> argtypes; every function returns int except the two noted below
+SIGNATURES = {
+    'b200ov_init': [_I],
+    'b200ov_device_info': [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_Z)],
+    'b200ov_malloc': [C.POINTER(_P), _Z],
+    'b200ov_free': [_P],
+    'b200ov_host_alloc': [C.POINTER(_P), _Z],
+    'b200ov_host_free': [_P],
+    'b200ov_memcpy_h2d': [_P, _P, _Z, _P],
+    'b200ov_memcpy_d2h': [_P, _P, _Z, _P],
+    'b200ov_memcpy_d2d': [_P, _P, _Z, _P],
+    'b200ov_memset': [_P, _I, _Z, _P],
+    'b200ov_stream_create': [C.POINTER(_P)],
+    'b200ov_stream_destroy': [_P],
+    'b200ov_stream_sync': [_P],
+    'b200ov_graph_begin': [_P],
+    'b200ov_graph_end': [_P, C.POINTER(_P)],
+    'b200ov_graph_launch': [_P, _P],
+    'b200ov_graph_destroy': [_P],
+    'b200ov_conv_weight_dims': [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)],
+    'b200ov_pack_conv_weights': [_P, _P, _I, _I, _I, _I, _P],
+    'b200ov_conv2d': [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
+    'b200ov_matmul': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P],
+    'b200ov_pack_dw_weights': [_P, _P, _I, _I, _I, _P],
+    'b200ov_dwconv2d': [C.POINTER(DwConvDesc), _P, _P, _P, _P, _P],
+    'b200ov_pool2d': [C.POINTER(PoolDesc), _P, _P, _P, _P, _P],
+    'b200ov_affine_act': [_P, _P, _L, _I, _I, _I, _I, _P, _F, _I, _P, _F, _I, _F, _F, _P],
+    'b200ov_binary': [_I, _P, _P, _P, _L, _P],
+    'b200ov_softmax': [_P, _P, _I, _I, _P],
+    'b200ov_lrn': [_P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200ov_transpose': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'b200ov_nchw_to_nhwc_affine': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _F, _P],
+    'b200ov_copy2d': [_P, _P, _L, _I, _I, _I, _P],
+}
+NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
+
+_lib = None
+launch_count = 0          # kernels launched through this binding (bench.py reports it)
+
+_LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_matmul', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
+              'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_transpose',
+              'b200ov_nchw_to_nhwc_affine', 'b200ov_copy2d'}
+
+
+def load():
+    """dlopen libb200ov.so and declare every prototype.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise B200ovError('libb200ov.so is not built ({}); run `python -m pyopenvino_b200.build`. '
+                          'pyopenvino_b200 has no CPU fallback.'.format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _I
+    for name, (args, res) in NON_STATUS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().b200ov_last_error().decode('utf-8', 'replace')
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; non-zero status becomes a Python exception."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    if rc != OK:
+        raise B200ovError('{} failed (code {}): {}'.format(name, rc, last_error()))
+    if name in _LAUNCHING:
+        launch_count += 1
+    return rc

@@ -1,0 +1,66 @@
+// b200ov_conv2d / b200ov_matmul: descriptor validation and kernel-family dispatch.
+#include "common.cuh"
+
+namespace b200ov {
+int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y, cudaStream_t s);
+// tcgen05 path (gemm_tcgen05.cu): returns B200OV_ERR_UNSUPPORTED when the shape is not eligible
+int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
+                   cudaStream_t s, bool probe_only);
+}  // namespace b200ov
+
+using namespace b200ov;
+
+static int validate(const b200ov_conv_desc* d, const float* x, const float* wp, float* y) {
+  B200OV_REQUIRE(d && x && wp && y, "conv2d: null argument");
+  B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv2d: bad tensor dims");
+  B200OV_REQUIRE(d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 && d->pt >= 0 && d->pl >= 0, "conv2d: bad filter geometry");
+  B200OV_REQUIRE(d->oh > 0 && d->ow > 0, "conv2d: bad output size");
+  B200OV_REQUIRE(d->x_ld >= d->cin && d->y_ld >= d->cout, "conv2d: channel pitch smaller than channel count");
+  B200OV_REQUIRE(d->ldw >= d->cout && d->ldw % 64 == 0, "conv2d: weights are not in packed form (ldw %d)", d->ldw);
+  B200OV_REQUIRE(d->act >= B200OV_ACT_NONE && d->act <= B200OV_ACT_SIGMOID, "conv2d: bad activation");
+  // the last window must start inside the zero-padded image
+  B200OV_REQUIRE((d->oh - 1) * d->sh - d->pt < d->h && (d->ow - 1) * d->sw - d->pl < d->w,
+                 "conv2d: output size inconsistent with input / stride / pads");
+  return B200OV_OK;
+}
+
+extern "C" {
+
+int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias, float* y,
+                  void* stream) {
+  int rc = validate(d, x, w_packed, y);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  switch (d->math) {
+    case B200OV_MATH_FP32:
+      return conv2d_ffma(d, x, w_packed, bias, y, s);
+    case B200OV_MATH_TF32X3:
+    case B200OV_MATH_TF32:
+      return conv2d_tcgen05(d, x, w_packed, bias, y, s, false);
+    case B200OV_MATH_AUTO: {
+      if (conv2d_tcgen05(d, x, w_packed, bias, y, s, true) == B200OV_OK) {
+        b200ov_conv_desc dd = *d;
+        dd.math = B200OV_MATH_TF32X3;
+        return conv2d_tcgen05(&dd, x, w_packed, bias, y, s, false);
+      }
+      return conv2d_ffma(d, x, w_packed, bias, y, s);
+    }
+    default:
+      return set_error(B200OV_ERR_INVALID, "conv2d: unknown math mode %d", d->math);
+  }
+}
+
+int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw, const float* bias,
+                  int act, float act_lo, float act_hi, int math, float* y, int ldy, void* stream) {
+  B200OV_REQUIRE(m >= 0 && n > 0 && k > 0, "matmul: bad dims");
+  b200ov_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  // rows of A are the "pixels" of a 1x1 convolution over a 1 x m image with k channels
+  d.n = 1; d.h = 1; d.w = m > 0 ? m : 1; d.cin = k; d.cout = n; d.kh = 1; d.kw = 1; d.sh = 1; d.sw = 1;
+  d.pt = 0; d.pl = 0; d.oh = 1; d.ow = m > 0 ? m : 1; d.x_ld = lda; d.y_ld = ldy; d.ldw = ldw;
+  d.act = act; d.act_lo = act_lo; d.act_hi = act_hi; d.math = math;
+  if (m == 0) return B200OV_OK;
+  return b200ov_conv2d(&d, a, b_packed, bias, y, stream);
+}
+
+}  // extern "C"

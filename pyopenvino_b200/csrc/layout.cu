@@ -1,0 +1,110 @@
+// Layout glue: batched 2-D transpose (NCHW <-> NHWC, MatMul transpose flags), the fused
+// Parameter pre-processing (NCHW -> NHWC with per-channel scale / shift) and strided row copies
+// (Concat when a producer could not write in place).  All bandwidth-bound; the transposes go
+// through a padded 32x32 shared-memory tile so both the read and the write are coalesced.
+#include "common.cuh"
+
+namespace b200ov {
+
+// x: [batch][rows][x_ld] (cols valid)  ->  y: [batch][cols][y_ld] (rows valid)
+// AFFINE: v = v*scale[row] + shift[row] (row = source row = channel of an NCHW tensor)
+template <bool AFFINE>
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int rows,
+                                                        int cols, int x_ld, int y_ld, int tiles_r, int tiles_c,
+                                                        int has_scale, const float* __restrict__ scale_vec,
+                                                        float scale_s, int has_shift,
+                                                        const float* __restrict__ shift_vec, float shift_s) {
+  __shared__ float tile[32][33];
+  long long bid = blockIdx.x;
+  const int tc = (int)(bid % tiles_c);
+  bid /= tiles_c;
+  const int tr = (int)(bid % tiles_r);
+  const int b = (int)(bid / tiles_r);
+  const float* xb = x + (long long)b * rows * x_ld;
+  float* yb = y + (long long)b * cols * y_ld;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    int r = tr * 32 + ty + i, c = tc * 32 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = __ldg(xb + (long long)r * x_ld + c);
+      if (AFFINE) {
+        if (has_scale) v = __fmul_rn(v, scale_vec ? __ldg(scale_vec + r) : scale_s);
+        if (has_shift) v = __fadd_rn(v, shift_vec ? __ldg(shift_vec + r) : shift_s);
+      }
+    }
+    tile[ty + i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    int c = tc * 32 + ty + i, r = tr * 32 + tx;
+    if (r < rows && c < cols) yb[(long long)c * y_ld + r] = tile[tx][ty + i];
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                     long long rows, int cols, int src_ld, int dst_ld) {
+  const int cg = cols / V;
+  const long long total = rows * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cg;
+    const int c0 = (int)(idx - r * cg) * V;
+    if constexpr (V == 4)
+      *reinterpret_cast<float4*>(dst + r * dst_ld + c0) = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c0));
+    else
+      dst[r * dst_ld + c0] = __ldg(src + r * src_ld + c0);
+  }
+}
+
+static int launch_transpose(bool affine, const float* x, float* y, int batch, int rows, int cols, int x_ld, int y_ld,
+                            int has_scale, const float* scale_vec, float scale_s, int has_shift,
+                            const float* shift_vec, float shift_s, cudaStream_t s) {
+  int tiles_r = ceil_div(rows, 32), tiles_c = ceil_div(cols, 32);
+  long long blocks = (long long)batch * tiles_r * tiles_c;
+  if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "transpose: grid too large");
+  if (blocks == 0) return B200OV_OK;
+  if (affine)
+    transpose_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, has_scale,
+                                                           scale_vec, scale_s, has_shift, shift_vec, shift_s);
+  else
+    transpose_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr,
+                                                            0.f, 0, nullptr, 0.f);
+  B200OV_LAUNCH_CHECK("transpose_kernel");
+  return B200OV_OK;
+}
+
+}  // namespace b200ov
+
+using namespace b200ov;
+
+extern "C" {
+
+int b200ov_transpose(const float* x, float* y, int batch, int rows, int cols, int x_ld, int y_ld, void* stream) {
+  B200OV_REQUIRE(x && y && batch >= 0 && rows > 0 && cols > 0 && x_ld >= cols && y_ld >= rows, "transpose: bad argument");
+  return launch_transpose(false, x, y, batch, rows, cols, x_ld, y_ld, 0, nullptr, 0.f, 0, nullptr, 0.f, as_stream(stream));
+}
+
+int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, int y_ld, int has_scale,
+                               const float* scale_vec, float scale_s, int has_shift, const float* shift_vec,
+                               float shift_s, void* stream) {
+  B200OV_REQUIRE(x && y && n >= 0 && c > 0 && hw > 0 && y_ld >= c, "nchw_to_nhwc_affine: bad argument");
+  return launch_transpose(true, x, y, n, c, hw, hw, y_ld, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s,
+                          as_stream(stream));
+}
+
+int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream) {
+  B200OV_REQUIRE(src && dst && rows >= 0 && cols > 0 && src_ld >= cols && dst_ld >= cols, "copy2d: bad argument");
+  if (rows == 0) return B200OV_OK;
+  const bool vec = (cols % 4 == 0) && (src_ld % 4 == 0) && (dst_ld % 4 == 0) && aligned16(src) && aligned16(dst);
+  cudaStream_t s = as_stream(stream);
+  if (vec) copy2d_kernel<4><<<bw_grid(rows * (cols / 4), 256), 256, 0, s>>>(src, dst, rows, cols, src_ld, dst_ld);
+  else copy2d_kernel<1><<<bw_grid(rows * cols, 256), 256, 0, s>>>(src, dst, rows, cols, src_ld, dst_ld);
+  B200OV_LAUNCH_CHECK("copy2d_kernel");
+  return B200OV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,647 @@
+"""pyopenvino_b200 inference engine: the reference's `IECore / read_network / load_network / infer`
+surface (`pyopenvino/inference_engine.py`) over HBM-resident feature maps and libb200ov kernels.
+
+Kept from the reference:
+  * `IECore()` discovers one plugin module per IR layer type, file basename == type string
+    (`inference_engine.py:23-43`); every node is executed through
+    `plugins[type].compute(node, inputs, kernel_type=..., debug=False)` (`:280`).
+  * `read_network(model, weights)` -> `IENetwork` with `.G` (networkx.DiGraph, node-attribute schema
+    of `README.md:88-125`, edges carry `connection=(from, fport, to, tport)`), `.inputs`, `.outputs`,
+    `.layers`, `.edges` (`:94-207`).
+  * `load_network(network, device_name, num_requests)` -> `Executable_Network` with
+    `.kernel_type`, `.expected_result`, `.pickle_node_args`, `.schedule_tasks()`,
+    `.infer({name: array}, verbose) -> {result_name: ndarray}` (`:211-321`).
+
+New, B200-side behaviour:
+  * what flows along the edges is a `DeviceArray` (NHWC in HBM), not a host ndarray; the only
+    host<->device copies are at Parameter and Result.
+  * `load_network(..., batch_size=B)` re-batches the static IR (the reference is batch-1 only); the
+    batched meaning is "B independent batch-1 results" (SURVEY.md section 0.4).
+  * a fusion plan folds Add / ReLU / Clamp / Multiply nodes into producer epilogues and lets Concat
+    producers write in place; the whole launch sequence is captured once into a CUDA graph and
+    replayed (`fuse`, `use_graph`).  `fuse=False, use_graph=False` gives the reference's node-by-node
+    behaviour with every node output materialised (used for per-node parity tests).
+There is no CPU execution path: `device_name` is accepted and ignored like in the reference
+(`inference_engine.py:86-90`), and everything runs on the current CUDA device.
+"""
+import glob
+import importlib
+import os
+import pickle
+import sys
+import time
+import xml.etree.ElementTree as et
+
+import networkx as nx
+import numpy as np
+
+from . import common_def
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_PLUGIN_DIR = os.path.join(_PKG_DIR, 'op_plugins')
+_PLUGIN_PKG = __name__.rsplit('.', 1)[0] + '.op_plugins'
+
+
+# -------------------------------------------------------------------------------------------------
+
+class Plugins:
+    """Operator-plugin registry: module file basename == IR layer type."""
+
+    def __init__(self):
+        self.plugins = {}
+
+    def import_plugin(self, plugin_path: str, file_path: str, plugin_name: str = None):
+        bname = os.path.splitext(os.path.basename(file_path))[0]
+        if plugin_name is None:
+            plugin_name = bname
+        module = importlib.import_module(plugin_path.replace('/', '.') + '.' + bname)
+        setattr(self, plugin_name, module)
+        self.plugins[plugin_name] = module
+
+    def load_plugins(self, plugin_path: str = None):
+        """Import every `<Type>.py` under the plugin directory (default: this package's op_plugins)."""
+        directory = _PLUGIN_DIR if plugin_path is None else plugin_path
+        package = _PLUGIN_PKG if plugin_path is None else plugin_path
+        for path in sorted(glob.glob(os.path.join(directory, '**', '*.py'), recursive=True)):
+            if os.path.basename(path).startswith('_'):
+                continue
+            self.import_plugin(package, path)
+
+
+class IECore:
+    def __init__(self):
+        self.plugins = Plugins()
+        self.plugins.load_plugins()
+        common_def.enable_escape_sequence()
+
+    def construct_node_info(self, net, node_type: str) -> list:
+        return [net.G.nodes[node_id] for node_id, _ in net.find_node_by_type(node_type)]
+
+    def check_nodes(self, G: nx.DiGraph):
+        unsupported = {G.nodes[n]['type'] for n in G.nodes if G.nodes[n]['type'] not in self.plugins.plugins}
+        if unsupported:
+            print('\x1b[31mUnsupported nodes : {}\x1b[37m'.format(unsupported))
+        return unsupported
+
+    # OpenVINO Inference Engine API
+    def read_network(self, model: str, weights: str = None):
+        net = IENetwork(self)
+        net.read_IR_Model(model)
+        net.parse_IR_XML()
+        net.build_graph()
+        net.set_constants_to_graph()
+        net.inputs = self.construct_node_info(net, 'Parameter')
+        net.outputs = self.construct_node_info(net, 'Result')
+        return net
+
+    # OpenVINO Inference Engine API
+    def load_network(self, network, device_name: str = 'B200', num_requests: int = 1, batch_size: int = None,
+                     fuse: bool = True, use_graph: bool = True):
+        if batch_size is not None and batch_size != network.batch_size:
+            network.set_batch_size(batch_size)
+        exenet = Executable_Network(network, fuse=fuse, use_graph=use_graph)
+        self.check_nodes(exenet.ienet.G)
+        exenet.schedule_tasks()
+        return exenet
+
+
+# -------------------------------------------------------------------------------------------------
+
+class IENetwork:
+    def __init__(self, iecore: IECore):
+        self.ie = iecore
+        self.xml = None
+        self.bin = None
+        self.G = None
+        self.layers = None
+        self.edges = None
+        self.inputs = None
+        self.outputs = None
+        self.batch_size = 1
+
+    def read_IR_Model(self, model):
+        bname, ext = os.path.splitext(model)
+        xml_file, bin_file = bname + '.xml', bname + '.bin'
+        if not os.path.isfile(xml_file) or not os.path.isfile(bin_file):
+            raise Exception('model {} is not found'.format(model))
+        self.xml = et.parse(xml_file)
+        with open(bin_file, 'rb') as f:
+            self.bin = f.read()
+
+    def parse_IR_XML(self):
+        root = self.xml.getroot()
+        if root.tag != 'net':
+            raise Exception('Not an OpenVINO IR file')
+        layers = {}
+        for layer in root.findall('./layers/layer'):
+            info = {key: val for key, val in layer.attrib.items() if key != 'id'}
+            data = layer.find('data')
+            if data is not None:
+                info['data'] = dict(data.attrib)
+                for key in ('shape', 'stride'):
+                    if key in info['data']:
+                        text = info['data'][key]
+                        info['data'][key] = common_def.string_to_tuple(text) if text.strip() else ()
+            for tag in ('input', 'output'):
+                ports = layer.find(tag)
+                if ports is not None:
+                    info[tag] = {}
+                    for port in ports.findall('port'):
+                        dims = tuple(int(dim.text) for dim in port.findall('./dim'))
+                        info[tag][int(port.attrib['id'])] = {'precision': port.attrib['precision'], 'dims': dims}
+            layers[int(layer.attrib['id'])] = info
+        self.layers = layers
+        self.edges = [(int(e.attrib['from-layer']), int(e.attrib['from-port']), int(e.attrib['to-layer']),
+                       int(e.attrib['to-port'])) for e in root.findall('./edges/edge')]
+
+    def build_graph(self):
+        self.G = nx.DiGraph()
+        for node_id, node_info in self.layers.items():
+            self.G.add_node(node_id)
+            for key, val in node_info.items():
+                self.G.nodes[node_id][key] = val
+        for edge in self.edges:
+            self.G.add_edge(edge[0], edge[2])
+            self.G.edges[(edge[0], edge[2])]['connection'] = edge
+        assert nx.is_directed_acyclic_graph(self.G)
+
+    def set_constants_to_graph(self):
+        """Slice every Const blob out of the `.bin` as an ndarray view (the reference unpacks python
+        tuples here, `inference_engine.py:188-199`)."""
+        for node_id, _ in self.find_node_by_type('Const'):
+            node = self.G.nodes[node_id]
+            data = node['data']
+            offset, size = int(data['offset']), int(data['size'])
+            precision = data['element_type'].upper()
+            dtype = np.dtype(common_def.type_convert_tbl[data['element_type']])
+            decoded = np.frombuffer(self.bin, dtype=dtype, count=size // dtype.itemsize, offset=offset)
+            node['const'] = {'data': decoded, 'element_info': precision, 'size': size,
+                             'decode_info': common_def.format_config[precision]}
+
+    def find_node_by_type(self, type: str) -> list:
+        return [(n, self.G.nodes[n]['name']) for n in self.G.nodes() if self.G.nodes[n]['type'] == type]
+
+    # ---- batching (new: the reference has no reshape API) ---------------------------------------
+    def set_batch_size(self, batch: int):
+        """Rewrite the static shapes for `batch` images per inference.
+
+        Every tensor downstream of a Parameter gets dim 0 multiplied by batch / old batch.  ShapeOf
+        outputs are static shape vectors and stop the propagation.  DetectionOutput emits
+        (1, 1, N*keep_top_k, 7) (`DetectionOutput.py:232-237`), so its dim 2 scales instead.
+        """
+        assert batch >= 1 and self.batch_size >= 1
+        G = self.G
+        dynamic = set()
+        stack = [n for n in G.nodes if G.nodes[n]['type'] == 'Parameter']
+        while stack:
+            n = stack.pop()
+            if n in dynamic or G.nodes[n]['type'] == 'ShapeOf':
+                continue
+            dynamic.add(n)
+            stack.extend(G.successors(n))
+        old = self.batch_size
+
+        def scale(dims, axis):
+            dims = list(dims)
+            assert dims[axis] % old == 0
+            dims[axis] = dims[axis] // old * batch
+            return tuple(dims)
+
+        for n in dynamic:
+            node = G.nodes[n]
+            axis = 2 if node['type'] == 'DetectionOutput' else 0
+            for port in node.get('output', {}).values():
+                if len(port['dims']) > axis:
+                    port['dims'] = scale(port['dims'], axis)
+            if node['type'] == 'Parameter':
+                node['data']['shape'] = scale(node['data']['shape'], 0)
+        for fl, fp, tl, tp in self.edges:
+            if fl in dynamic:
+                G.nodes[tl]['input'][tp]['dims'] = G.nodes[fl]['output'][fp]['dims']
+        self.batch_size = batch
+
+
+# -------------------------------------------------------------------------------------------------
+
+_EPILOGUE_HEADS = ('Convolution', 'GroupConvolution', 'MatMul')
+_OUT_CAPABLE = ('Convolution', 'GroupConvolution', 'MaxPool', 'AvgPool', 'LRN', 'ReLU', 'Clamp', 'Sigmoid')
+
+
+class Executable_Network:
+    def __init__(self, ienetwork: IENetwork, fuse: bool = True, use_graph: bool = True):
+        self.ienet = ienetwork
+        self.expected_result = None     # {node_name: [precision, dims, ndarray]} feature-map ground truth (debug)
+        self.kernel_type = 'naive'      # accepted for compatibility: every value runs the CUDA kernels
+        self.pickle_node_args = []      # node ids whose (node, inputs) are pickled for node unit tests (eager mode)
+        self.fuse = fuse
+        self.use_graph = use_graph
+        self.task_list = []
+        self.stream = None
+        self._plan = None
+        self._graph = None
+        self._graph_key = None
+        self._arena = None
+        self._static_in = {}
+        self._static_out = {}
+        self._user_inputs = {}
+        self._graph_launches = 0
+        self.last_node_seconds = {}
+
+    # ---- scheduling (inference_engine.py:218-242) -------------------------------------------------
+    def schedule_tasks(self):
+        G = self.ienet.G
+        done, pending = set(), []
+        self.task_list = []
+        for node_id in G.nodes:
+            if G.nodes[node_id]['type'] in ('Const', 'Parameter'):
+                self.task_list.append(node_id)
+                done.add(node_id)
+            else:
+                pending.append(node_id)
+        while pending:
+            rest = []
+            for node_id in pending:
+                if all(p in done for p in G.predecessors(node_id)):
+                    self.task_list.append(node_id)
+                    done.add(node_id)
+                else:
+                    rest.append(node_id)
+            assert len(rest) < len(pending)
+            pending = rest
+        self._plan = None
+        self._graph = None
+
+    def prepare_inputs_for_task(self, task) -> dict:
+        G = self.ienet.G
+        inputs = {}
+        for predecessor in G.pred[task]:
+            fl, fp, tl, tp = G.edges[(predecessor, task)]['connection']
+            inputs[tp] = G.nodes[fl]['output'][fp].get('data')
+        return inputs
+
+    # ---- fusion plan -------------------------------------------------------------------------------
+    def _const_operand(self, consumer, producer):
+        """(node_id of the Const feeding `consumer` on its other port, that Const's dims) or None."""
+        G = self.ienet.G
+        others = [p for p in G.pred[consumer] if p != producer]
+        if len(others) != 1 or G.nodes[others[0]]['type'] != 'Const':
+            return None
+        return others[0]
+
+    def _single_consumer(self, node_id):
+        G = self.ienet.G
+        # ShapeOf only reads the static port dims (ShapeOf.py:21), so it does not count as a data consumer
+        succ = [n for n in G.successors(node_id) if G.nodes[n]['type'] != 'ShapeOf']
+        return succ[0] if len(succ) == 1 else None
+
+    def _per_channel(self, const_id, channels, like_dims):
+        """True if the Const broadcasts per channel (or is a scalar) against a tensor of `like_dims`."""
+        dims = tuple(self.ienet.G.nodes[const_id]['data']['shape'])
+        size = int(np.prod(dims)) if len(dims) else 1
+        if size == 1:
+            return True
+        if size != channels:
+            return False
+        if len(like_dims) == 4:
+            return len(dims) == 4 and dims[1] == channels
+        return dims[-1] == channels
+
+    def build_plan(self):
+        """Decide, per node, what is folded into whom.  Result: self._plan = {node_id: step} with
+        step = {'skip': bool, 'fused': {...const node ids...}, 'store_as': node_id, 'concat': (cid, off)}."""
+        G = self.ienet.G
+        plan = {n: {'skip': False, 'ops': {}, 'store_as': n, 'out_slot': None} for n in self.task_list}
+        if not self.fuse:
+            self._plan = plan
+            return plan
+        absorbed = set()
+
+        def absorb(head, node):
+            plan[node]['skip'] = True
+            absorbed.add(node)
+            plan[head]['store_as'] = node
+
+        for n in self.task_list:
+            if n in absorbed:
+                continue
+            node = G.nodes[n]
+            t = node['type']
+            if 'output' not in node:
+                continue
+            out_dims = node['output'][common_def.first_output_port(node)]['dims']
+            ops = plan[n]['ops']
+            tail = n
+            if t in _EPILOGUE_HEADS:
+                channels = out_dims[1] if len(out_dims) == 4 else out_dims[-1]
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] == 'Add':
+                    c = self._const_operand(nxt, tail)
+                    conn = G.edges[(tail, nxt)]['connection']
+                    if c is not None and conn[3] == 0 and self._per_channel(c, channels, out_dims) and \
+                            int(np.prod(G.nodes[c]['data']['shape'])) == channels:
+                        ops['bias'] = c
+                        absorb(n, nxt)
+                        tail = nxt
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] in ('ReLU', 'Clamp'):
+                    nn = G.nodes[nxt]
+                    ops['act'] = ('relu',) if nn['type'] == 'ReLU' else ('clamp', float(nn['data']['min']), float(nn['data']['max']))
+                    absorb(n, nxt)
+                    tail = nxt
+            elif t == 'MaxPool':
+                channels = out_dims[1]
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] == 'Multiply':
+                    c = self._const_operand(nxt, tail)
+                    if c is not None and int(np.prod(G.nodes[c]['data']['shape'])) == channels and \
+                            self._per_channel(c, channels, out_dims):
+                        ops['scale'] = c
+                        absorb(n, nxt)
+                        tail = nxt
+                        nxt2 = self._single_consumer(tail)
+                        if nxt2 is not None and G.nodes[nxt2]['type'] == 'Add':
+                            c2 = self._const_operand(nxt2, tail)
+                            conn = G.edges[(tail, nxt2)]['connection']
+                            if c2 is not None and conn[3] == 0 and int(np.prod(G.nodes[c2]['data']['shape'])) == channels \
+                                    and self._per_channel(c2, channels, out_dims):
+                                ops['shift'] = c2
+                                absorb(n, nxt2)
+                                tail = nxt2
+            elif t == 'Parameter' and len(out_dims) == 4:
+                channels = out_dims[1]
+                ops['to_nhwc'] = True
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] == 'Multiply':
+                    c = self._const_operand(nxt, tail)
+                    if c is not None and self._per_channel(c, channels, out_dims):
+                        ops['scale'] = c
+                        absorb(n, nxt)
+                        tail = nxt
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] == 'Add':
+                    c = self._const_operand(nxt, tail)
+                    conn = G.edges[(tail, nxt)]['connection']
+                    if c is not None and conn[3] == 0 and self._per_channel(c, channels, out_dims):
+                        ops['shift'] = c
+                        absorb(n, nxt)
+                        tail = nxt
+        # Concat in place: producers whose only consumer is a channel Concat write into its buffer
+        for n in self.task_list:
+            node = G.nodes[n]
+            if node['type'] != 'Concat' or int(node['data']['axis']) != 1:
+                continue
+            out_dims = node['output'][common_def.first_output_port(node)]['dims']
+            if len(out_dims) != 4:
+                continue
+            slots = {}
+            off = 0
+            for pred in G.pred[n]:       # same order the Concat plugin sees its inputs
+                fl, fp, tl, tp = G.edges[(pred, n)]['connection']
+                c = G.nodes[fl]['output'][fp]['dims'][1]
+                slots[fl] = (off, c)
+                off += c
+            plan[n]['concat_slots'] = slots
+            for tail_id, (coff, c) in slots.items():
+                head = next((h for h in self.task_list if plan[h]['store_as'] == tail_id and not plan[h]['skip']), None)
+                if head is None or G.out_degree(tail_id) != 1 or G.nodes[head]['type'] not in _OUT_CAPABLE:
+                    continue
+                if G.nodes[head]['type'] in ('ReLU', 'Clamp', 'Sigmoid', 'LRN') and head != tail_id:
+                    continue
+                plan[head]['out_slot'] = (n, coff, c)
+        self._plan = plan
+        return plan
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def _ensure_device(self):
+        from . import device as dev
+        import torch
+        dev.init()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        return dev
+
+    def _run(self, verbose=False, capture=False):
+        """One pass over the task list.  In planned mode folded nodes are skipped and constants are
+        evaluated once (first pass) and kept."""
+        from . import kernels
+        from .device import is_device
+        G = self.ienet.G
+        p = self.ienet.ie.plugins
+        plan = self._plan if self._plan is not None else self.build_plan()
+        concat_bufs = {}
+        for task in self.task_list:
+            node = G.nodes[task]
+            step = plan[task]
+            if step['skip']:
+                continue
+            node_type = node['type']
+            if node_type not in p.plugins:
+                print('ERROR: Operation \'{}\' (node={}) is not supported.'.format(node_type, node['name']))
+                sys.exit(-1)
+            if step.get('const_done'):
+                continue
+            inputs = self.prepare_inputs_for_task(task) if 'input' in node else {}
+            fused = {}
+            for key, val in step['ops'].items():
+                if key in ('bias', 'scale', 'shift'):
+                    fused[key] = G.nodes[val]['output'][0]['data']
+                else:
+                    fused[key] = val
+            if step['out_slot'] is not None:
+                cid, coff, c = step['out_slot']
+                if cid not in concat_bufs:
+                    n_, c_, h_, w_ = G.nodes[cid]['output'][common_def.first_output_port(G.nodes[cid])]['dims']
+                    concat_bufs[cid] = kernels.new_nhwc(n_, c_, h_, w_)
+                fused['out'] = kernels.channel_slice(concat_bufs[cid], coff, c)
+            if node_type == 'Concat' and 'concat_slots' in step and self.fuse:
+                if task not in concat_bufs:
+                    n_, c_, h_, w_ = node['output'][common_def.first_output_port(node)]['dims']
+                    concat_bufs[task] = kernels.new_nhwc(n_, c_, h_, w_)
+                buf = concat_bufs[task]
+                for src, (coff, c) in step['concat_slots'].items():
+                    src_head = next((h for h in plan if plan[h]['store_as'] == src and not plan[h]['skip']), None)
+                    if src_head is None or plan[src_head]['out_slot'] is None or plan[src_head]['out_slot'][0] != task:
+                        port = [conn for conn in (G.edges[(src, task)]['connection'],)][0][1]
+                        kernels.copy_channels(kernels.as_nhwc(G.nodes[src]['output'][port]['data']),
+                                              kernels.channel_slice(buf, coff, c))
+                fused['inplace'] = buf
+            if capture and node_type == 'Result':
+                x = inputs[0]
+                self._static_out[node['name']] = kernels.as_plain(x) if is_device(x) else x
+                continue
+            if verbose:
+                print('{}, {}, {}, '.format(task, node_type, node['name']), end=' ', flush=True)
+            if task in self.pickle_node_args and not capture:
+                with open('node_args_{}.pickle'.format(task), 'wb') as f:
+                    host_inputs = {k: (np.asarray(v) if is_device(v) else v) for k, v in inputs.items()}
+                    pickle.dump(({k: v for k, v in node.items() if k not in ('output', 'const')}, host_inputs), file=f)
+            stime = time.time()
+            if fused:
+                res = p.plugins[node_type].compute(node, inputs, kernel_type=self.kernel_type, debug=False, fused=fused)
+            else:
+                res = p.plugins[node_type].compute(node, inputs, kernel_type=self.kernel_type, debug=False)
+            if verbose:
+                import torch
+                torch.cuda.current_stream().synchronize()
+                etime = time.time()
+                print(etime - stime)
+                self.last_node_seconds[node['name']] = etime - stime
+            if self.expected_result is not None and node['name'] in self.expected_result and len(res) > 0:
+                out_data = np.asarray(next(iter(res.values())))
+                gt = np.asarray(self.expected_result[node['name']][2]).astype(out_data.dtype)
+                ok = out_data.shape == gt.shape and np.allclose(out_data, gt, rtol=1e-4, atol=1e-5)
+                print('{}{} : {} / {}\x1b[37m'.format('\x1b[32m' if ok else '\x1b[31m', node['name'], out_data.shape, gt.shape))
+            if len(res) > 0:
+                target = G.nodes[step['store_as']]
+                for port_id, data in res.items():
+                    tport = port_id if step['store_as'] == task else common_def.first_output_port(target)
+                    target['output'][tport]['data'] = data
+
+    def run_tasks(self, verbose: bool = False):
+        """Eager pass: every scheduled node through its plugin (inference_engine.py:259-292)."""
+        self._run(verbose=verbose, capture=False)
+
+    def _mark_constants(self):
+        """Evaluate input-independent nodes once (weights upload, SSD prior-box branch) and keep them."""
+        G = self.ienet.G
+        plan = self._plan
+        const_nodes = set()
+        for task in self.task_list:
+            t = G.nodes[task]['type']
+            if t == 'Const' or t == 'ShapeOf':
+                const_nodes.add(task)
+            elif t not in ('Parameter', 'Result') and all(p in const_nodes for p in G.pred[task]) and G.in_degree(task) > 0:
+                const_nodes.add(task)
+        return const_nodes
+
+    # OpenVINO IE compatible API - Run inference
+    def infer(self, inputs: dict, verbose: bool = False) -> dict:
+        dev = self._ensure_device()
+        import torch
+        G = self.ienet.G
+        if self._plan is None:
+            self.build_plan()
+        graph_mode = self.use_graph and not verbose and not self.pickle_node_args and self.expected_result is None
+        self._user_inputs = dict(inputs)
+        if not graph_mode or self._graph is None:
+            for node_name, val in inputs.items():        # inference_engine.py:300-303
+                for node in G.nodes:
+                    if G.nodes[node]['name'] == node_name:
+                        G.nodes[node]['param'] = val
+        if verbose:
+            print('# node_id node_name time (sec)')
+        stime = time.time()
+        with torch.cuda.stream(self.stream):
+            if graph_mode:
+                res = self._infer_graph()
+            else:
+                self.run_tasks(verbose)
+                self.stream.synchronize()
+                res = {G.nodes[n]['name']: G.nodes[n]['result'] for n, _ in self.ienet.find_node_by_type('Result')}
+        etime = time.time()
+        if verbose:
+            print('@TOTAL_TIME,', etime - stime)
+        return res
+
+    # ---- CUDA-graph replay path ----------------------------------------------------------------------
+    def _param_nodes(self):
+        G = self.ienet.G
+        return [G.nodes[n] for n, _ in self.ienet.find_node_by_type('Parameter')]
+
+    def _prepare_graph(self):
+        """Warm-up (sizes the arena, uploads / packs constants) then capture the launch sequence."""
+        import ctypes as C
+        import torch
+        from . import _cabi, kernels
+        from . import device as dev
+        from .device import DeviceArray
+        G = self.ienet.G
+        # static input staging: pinned host + device buffers
+        self._static_in = {}
+        for node in self._param_nodes():
+            shape = tuple(node['data']['shape'])
+            n = int(np.prod(shape))
+            self._static_in[node['name']] = {
+                'host': torch.empty(n, dtype=torch.float32).pin_memory(),
+                'dev': DeviceArray(torch.empty(n, dtype=torch.float32, device='cuda'), shape, 'plain'),
+                'node': node}
+        # 1) constants: evaluated once, outside the arena, then frozen
+        consts = self._mark_constants()
+        dev.set_arena(None)
+        for task in self.task_list:
+            if task in consts and not self._plan[task].get('const_done'):
+                node = G.nodes[task]
+                if self._plan[task]['skip']:
+                    continue
+                inputs = self.prepare_inputs_for_task(task) if 'input' in node else {}
+                res = self.ienet.ie.plugins.plugins[node['type']].compute(node, inputs, kernel_type=self.kernel_type, debug=False)
+                for port_id, data in res.items():
+                    node['output'][port_id]['data'] = data
+                self._plan[task]['const_done'] = True
+        # 2) warm-up pass inside the arena (also packs weights: those allocations are persistent)
+        self._arena = dev.Arena()
+        self.stage_inputs(self._user_inputs)
+        for st in self._static_in.values():
+            st['node']['param'] = st['dev']
+        dev.set_arena(self._arena)
+        try:
+            self._arena.reset()
+            self._static_out = {}
+            self._run(capture=True)
+            self.stream.synchronize()
+            # 3) capture
+            self._arena.reset()
+            self._arena.frozen = True
+            self._static_out = {}
+            s = C.c_void_p(self.stream.cuda_stream)
+            launches0 = _cabi.launch_count
+            _cabi.call('b200ov_graph_begin', s)
+            try:
+                self._run(capture=True)
+            finally:
+                g = C.c_void_p(0)
+                _cabi.call('b200ov_graph_end', s, C.byref(g))
+            self._graph = g
+            self._graph_launches = _cabi.launch_count - launches0
+        finally:
+            dev.set_arena(None)
+        self._out_host = {name: torch.empty(max(arr.size, 1), dtype=torch.float32).pin_memory()
+                          for name, arr in self._static_out.items()}
+
+    def stage_inputs(self, inputs: dict = None):
+        """Copy host inputs (default: the arrays given to the last infer()) into the static device buffers."""
+        import torch
+        for name, st in self._static_in.items():
+            val = inputs[name] if inputs is not None and name in inputs else None
+            if val is None:
+                continue
+            a = np.asarray(val, dtype=np.float32).reshape(-1)
+            assert a.size == st['host'].numel(), 'input {} has {} elements, network expects {}'.format(name, a.size, st['host'].numel())
+            st['host'].numpy()[:] = a
+            st['dev'].t.copy_(st['host'], non_blocking=True)
+
+    def replay(self):
+        """Launch the captured graph on self.stream (inputs must already be staged)."""
+        import ctypes as C
+        from . import _cabi
+        _cabi.call('b200ov_graph_launch', self._graph, C.c_void_p(self.stream.cuda_stream))
+
+    def fetch_outputs(self):
+        res = {}
+        for name, arr in self._static_out.items():
+            self._out_host[name][:arr.size].copy_(arr.t[:arr.size], non_blocking=True)
+        self.stream.synchronize()
+        for name, arr in self._static_out.items():
+            res[name] = self._out_host[name][:arr.size].numpy().reshape(arr.shape).copy()
+        return res
+
+    def _infer_graph(self):
+        if self._graph is None:
+            self._prepare_graph()
+        self.stage_inputs(self._user_inputs)
+        self.replay()
+        return self.fetch_outputs()
+
+    def kernels_per_inference(self):
+        """Number of libb200ov kernel launches captured in the graph (0 before the first inference)."""
+        return getattr(self, '_graph_launches', 0)

@@ -1,0 +1,351 @@
+"""Thin Python wrappers: DeviceArray in, DeviceArray out, one libb200ov call each.
+
+This is the only module that talks to the C ABI for compute.  Nothing here does arithmetic on the
+host; numpy is used to stage host inputs for upload and nothing else.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import device as dev
+from .device import DeviceArray
+
+_ACTS = {None: _cabi.ACT_NONE, 'relu': _cabi.ACT_RELU, 'clamp': _cabi.ACT_CLAMP, 'sigmoid': _cabi.ACT_SIGMOID}
+default_math = _cabi.MATH_AUTO
+
+
+def _act(act):
+    """None | ('relu',) | ('clamp', lo, hi) | ('sigmoid',) -> (code, lo, hi)"""
+    if act is None:
+        return _cabi.ACT_NONE, 0.0, 0.0
+    kind = act[0]
+    if kind == 'clamp':
+        return _cabi.ACT_CLAMP, float(act[1]), float(act[2])
+    return _ACTS[kind], 0.0, 0.0
+
+
+def _p(x):
+    """device pointer (or NULL) as c_void_p"""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, DeviceArray):
+        return C.c_void_p(x.ptr)
+    return C.c_void_p(int(x))
+
+
+def _s():
+    return C.c_void_p(dev.stream())
+
+
+# ---- host <-> device ------------------------------------------------------------------------
+
+def upload(arr, keep_host=False):
+    """Host ndarray -> plain DeviceArray (one H2D copy on the current stream)."""
+    dev.init()
+    a = np.ascontiguousarray(arr, dtype=np.float32)
+    t = dev.alloc_f32(a.size)
+    if a.size:
+        t[:a.size].copy_(torch.from_numpy(a.reshape(-1)), non_blocking=False)
+    out = DeviceArray(t, a.shape, 'plain')
+    if keep_host:
+        out.cache['host'] = a
+    return out
+
+
+def as_device(x):
+    return x if isinstance(x, DeviceArray) else upload(x)
+
+
+def host_value(x):
+    """Small constant operand as a host ndarray (no device sync when the Const plugin cached it)."""
+    if isinstance(x, DeviceArray):
+        if 'host' not in x.cache:
+            x.cache['host'] = x.numpy()
+        return x.cache['host']
+    return np.asarray(x)
+
+
+def to_nhwc(x, scale=None, shift=None, out=None):
+    """plain NCHW -> NHWC (optionally y = x*scale[c] + shift[c] on the fly: fused Parameter pre-processing)."""
+    x = as_device(x)
+    assert x.layout == 'plain' and x.ndim == 4
+    n, c, h, w = x.shape
+    if out is None:
+        out = DeviceArray(dev.alloc_f32(n * h * w * c), x.shape, 'nhwc', ld=c)
+    sv, ss, hs = _affine_operand(scale, c)
+    bv, bs, hb = _affine_operand(shift, c)
+    _cabi.call('b200ov_nchw_to_nhwc_affine', _p(x), _p(out), n, c, h * w, out.ld, hs, sv, ss, hb, bv, bs, _s())
+    return out
+
+
+def to_plain(x):
+    """NHWC -> plain NCHW (the layout a host consumer or a flattening Reshape needs)."""
+    assert x.layout == 'nhwc'
+    n, c, h, w = x.shape
+    out = DeviceArray(dev.alloc_f32(n * c * h * w), x.shape, 'plain')
+    if h * w == 1 and x.is_dense():
+        _cabi.call('b200ov_copy2d', _p(x), _p(out), n, c, x.ld, c, _s())
+    else:
+        _cabi.call('b200ov_transpose', _p(x), _p(out), n, h * w, c, x.ld, h * w, _s())
+    return out
+
+
+def as_nhwc(x):
+    x = as_device(x)
+    if x.layout == 'nhwc':
+        return x
+    assert x.ndim == 4, 'expected a 4-D feature map, got shape {}'.format(x.shape)
+    return to_nhwc(x)
+
+
+def as_plain(x):
+    x = as_device(x)
+    return to_plain(x) if x.layout == 'nhwc' else x
+
+
+def new_nhwc(n, c, h, w):
+    return DeviceArray(dev.alloc_f32(n * h * w * c), (n, c, h, w), 'nhwc', ld=c)
+
+
+def _check_out(out, shape):
+    assert out.layout == 'nhwc' and tuple(out.shape) == tuple(shape), \
+        'preallocated output {} does not match result shape {}'.format(out, shape)
+    return out
+
+
+# ---- operands of the elementwise tail ----------------------------------------------------------
+
+def _affine_operand(b, c):
+    """-> (vector pointer or NULL, scalar value, has_flag) for a broadcast operand of `c` channels."""
+    if b is None:
+        return C.c_void_p(0), 0.0, 0
+    size = b.size
+    if size == 1:
+        return C.c_void_p(0), float(host_value(b).reshape(-1)[0]), 1
+    if size == c:
+        d = as_device(b)
+        assert d.layout == 'plain'
+        return C.c_void_p(d.ptr), 0.0, 1
+    raise _cabi.B200ovError('unsupported broadcast: operand with {} elements against {} channels'.format(size, c))
+
+
+def _vec_ptr(b, c):
+    if b is None:
+        return None
+    d = as_device(b)
+    assert d.layout == 'plain' and d.size == c, 'per-channel operand must have {} elements, got {}'.format(c, d.size)
+    return d
+
+
+# ---- Convolution / MatMul ----------------------------------------------------------------------
+
+class PackedWeights:
+    __slots__ = ('t', 'rows', 'ldw', 'cout', 'cin', 'kh', 'kw')
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+def pack_conv(w):
+    """OIHW (or [N][K] for MatMul) -> packed [kh*kw*cin][ldw]; cached on the weight array."""
+    w = as_device(w)
+    if 'conv' in w.cache:
+        return w.cache['conv']
+    assert w.layout == 'plain'
+    if w.ndim == 4:
+        cout, cin, kh, kw = w.shape
+    else:
+        cout, cin = w.shape
+        kh = kw = 1
+    rows, ldw = C.c_int(0), C.c_int(0)
+    _cabi.call('b200ov_conv_weight_dims', cout, cin, kh, kw, C.byref(rows), C.byref(ldw))
+    pk = PackedWeights()
+    # packed weights are long-lived: never from the per-inference arena
+    pk.t = torch.empty(rows.value * ldw.value, dtype=torch.float32, device='cuda')
+    pk.rows, pk.ldw, pk.cout, pk.cin, pk.kh, pk.kw = rows.value, ldw.value, cout, cin, kh, kw
+    _cabi.call('b200ov_pack_conv_weights', _p(w), C.c_void_p(pk.ptr), cout, cin, kh, kw, _s())
+    w.cache['conv'] = pk
+    return pk
+
+
+def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None):
+    x = as_nhwc(x)
+    pk = w if isinstance(w, PackedWeights) else pack_conv(w)
+    n, c, h, wd = x.shape
+    assert c == pk.cin, 'input has {} channels, filter expects {}'.format(c, pk.cin)
+    oh, ow = out_hw
+    shape = (n, pk.cout, oh, ow)
+    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
+    code, lo, hi = _act(act)
+    d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=pk.cout, kh=pk.kh, kw=pk.kw, sh=strides[0], sw=strides[1],
+                       pt=pads_begin[0], pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, ldw=pk.ldw,
+                       act=code, act_lo=lo, act_hi=hi, math=default_math if math is None else math)
+    b = _vec_ptr(bias, pk.cout)
+    _cabi.call('b200ov_conv2d', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(b), _p(out), _s())
+    return out
+
+
+def matmul(a, b, transpose_a=False, transpose_b=True, bias=None, act=None, math=None):
+    a = as_plain(a)
+    assert a.ndim == 2
+    if transpose_a:
+        k, m = a.shape
+        at = DeviceArray(dev.alloc_f32(m * k), (m, k), 'plain')
+        _cabi.call('b200ov_transpose', _p(a), _p(at), 1, k, m, m, k, _s())
+        a = at
+    m, k = a.shape
+    b = as_device(b)
+    key = 'mm_tb' if transpose_b else 'mm_plain'
+    if key not in b.cache:
+        if transpose_b:
+            nk = b                          # already [N][K]
+        else:
+            kk, nn = b.shape                # [K][N] -> [N][K]
+            nk = DeviceArray(torch.empty(kk * nn, dtype=torch.float32, device='cuda'), (nn, kk), 'plain')
+            _cabi.call('b200ov_transpose', _p(b), _p(nk), 1, kk, nn, nn, kk, _s())
+        b.cache[key] = pack_conv(nk)
+    pk = b.cache[key]
+    assert pk.cin == k, 'MatMul inner dims differ: {} vs {}'.format(k, pk.cin)
+    n = pk.cout
+    out = DeviceArray(dev.alloc_f32(m * n), (m, n), 'plain')
+    code, lo, hi = _act(act)
+    bv = _vec_ptr(bias, n)
+    _cabi.call('b200ov_matmul', m, n, k, _p(a), k, C.c_void_p(pk.ptr), pk.ldw, _p(bv), code, lo, hi,
+               default_math if math is None else math, _p(out), n, _s())
+    return out
+
+
+# ---- depthwise ---------------------------------------------------------------------------------
+
+def pack_dw(w):
+    w = as_device(w)
+    if 'dw' in w.cache:
+        return w.cache['dw']
+    g, co, ci, kh, kw = w.shape
+    if co != 1 or ci != 1:
+        raise _cabi.B200ovError('GroupConvolution: only depthwise (C_out/G = C_in/G = 1) is supported, like the reference')
+    t = torch.empty(g * kh * kw, dtype=torch.float32, device='cuda')
+    _cabi.call('b200ov_pack_dw_weights', _p(w), C.c_void_p(t.data_ptr()), g, kh, kw, _s())
+    w.cache['dw'] = (t, g, kh, kw)
+    return w.cache['dw']
+
+
+def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None):
+    x = as_nhwc(x)
+    t, g, kh, kw = pack_dw(w)
+    n, c, h, wd = x.shape
+    assert c == g, 'depthwise: {} input channels vs {} groups'.format(c, g)
+    oh, ow = out_hw
+    shape = (n, c, oh, ow)
+    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
+    code, lo, hi = _act(act)
+    d = _cabi.DwConvDesc(n=n, h=h, w=wd, c=c, kh=kh, kw=kw, sh=strides[0], sw=strides[1], pt=pads_begin[0],
+                         pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, act=code, act_lo=lo, act_hi=hi)
+    b = _vec_ptr(bias, c)
+    _cabi.call('b200ov_dwconv2d', C.byref(d), _p(x), C.c_void_p(t.data_ptr()), _p(b), _p(out), _s())
+    return out
+
+
+# ---- pooling -----------------------------------------------------------------------------------
+
+def pool2d(x, mode, kernel, strides, pads_begin, pads_end, out_hw, scale=None, shift=None, out=None):
+    x = as_nhwc(x)
+    n, c, h, wd = x.shape
+    oh, ow = out_hw
+    shape = (n, c, oh, ow)
+    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
+    d = _cabi.PoolDesc(n=n, h=h, w=wd, c=c, kh=kernel[0], kw=kernel[1], sh=strides[0], sw=strides[1],
+                       pt=pads_begin[0], pl=pads_begin[1], pb=pads_end[0], pr=pads_end[1], oh=oh, ow=ow,
+                       x_ld=x.ld, y_ld=out.ld, mode=mode)
+    _cabi.call('b200ov_pool2d', C.byref(d), _p(x), _p(_vec_ptr(scale, c)), _p(_vec_ptr(shift, c)), _p(out), _s())
+    return out
+
+
+# ---- elementwise tail ----------------------------------------------------------------------------
+
+def _rows_channels(x):
+    """(rows, channels, x_ld) view of an activation for channel-broadcast elementwise kernels."""
+    if x.layout == 'nhwc':
+        return x.pixels, x.shape[1], x.ld
+    c = x.shape[-1] if x.ndim >= 1 else 1
+    return x.size // max(c, 1), c, c
+
+
+def _like(x, out=None):
+    if out is not None:
+        return _check_out(out, x.shape)
+    if x.layout == 'nhwc':
+        n, c, h, w = x.shape
+        return new_nhwc(n, c, h, w)
+    return DeviceArray(dev.alloc_f32(x.size), x.shape, 'plain')
+
+
+def _channel_operand_ok(x, b):
+    """True when `b` broadcasts against `x` as a scalar or a per-channel vector in x's physical layout."""
+    if b.size == 1:
+        return True
+    bs = tuple(b.shape)
+    if x.layout == 'nhwc':
+        c = x.shape[1]
+        return b.size == c and len(bs) == 4 and bs[1] == c
+    # plain: channel = last dim
+    return b.size == x.shape[-1] and bs[-1] == x.shape[-1]
+
+
+def affine_act(x, scale=None, shift=None, act=None, out=None):
+    """act(x*scale + shift) with scalar / per-channel operands (either may be None)."""
+    x = as_device(x)
+    if x.layout == 'plain' and x.ndim == 4 and ((scale is not None and scale.size > 1) or (shift is not None and shift.size > 1)):
+        x = to_nhwc(x)
+    rows, c, x_ld = _rows_channels(x)
+    out = _like(x, out)
+    y_ld = out.ld if out.layout == 'nhwc' else c
+    sv, ss, hs = _affine_operand(scale, c)
+    bv, bs, hb = _affine_operand(shift, c)
+    code, lo, hi = _act(act)
+    _cabi.call('b200ov_affine_act', _p(x), _p(out), rows, c, x_ld, y_ld, hs, sv, ss, hb, bv, bs, code, lo, hi, _s())
+    return out
+
+
+def binary(op, a, b):
+    """Same-shape Add (op 0) / Multiply (op 1)."""
+    a, b = as_device(a), as_device(b)
+    assert tuple(a.shape) == tuple(b.shape)
+    if a.layout != b.layout or not a.is_dense() or not b.is_dense():
+        a, b = as_plain(a), as_plain(b)
+    out = _like(a)
+    _cabi.call('b200ov_binary', op, _p(a), _p(b), _p(out), a.size, _s())
+    return out
+
+
+def softmax_rows(x):
+    x = as_plain(x)
+    rows = x.shape[0] if x.ndim >= 2 else 1
+    cols = x.size // rows
+    out = DeviceArray(dev.alloc_f32(x.size), x.shape, 'plain')
+    _cabi.call('b200ov_softmax', _p(x), _p(out), rows, cols, _s())
+    return out
+
+
+def lrn(x, size, alpha, beta, bias, out=None):
+    x = as_nhwc(x)
+    out = _like(x, out)
+    _cabi.call('b200ov_lrn', _p(x), _p(out), x.pixels, x.shape[1], x.ld, out.ld, size, alpha, beta, bias, _s())
+    return out
+
+
+def copy_channels(src, dst):
+    """Copy an NHWC array into an NHWC channel slice of equal logical shape."""
+    assert src.layout == 'nhwc' and dst.layout == 'nhwc' and tuple(src.shape) == tuple(dst.shape)
+    _cabi.call('b200ov_copy2d', _p(src), _p(dst), src.pixels, src.shape[1], src.ld, dst.ld, _s())
+    return dst
+
+
+def channel_slice(buf, c_off, c):
+    """View of channels [c_off, c_off + c) of an NHWC buffer."""
+    n, ct, h, w = buf.shape
+    assert buf.layout == 'nhwc' and c_off + c <= ct
+    return DeviceArray(buf.t, (n, c, h, w), 'nhwc', ld=buf.ld, c_off=buf.c_off + c_off)
