@@ -76,26 +76,55 @@ def test_synthetic_models_vs_reference_golden(model_dir, model):
 
 @pytest.mark.parametrize('model', ['mnist_bn', 'googlenet-v1'])
 def test_every_node_vs_oracle(model_dir, model):
-    """Per-node parity with identical weights and input: eager unfused device run vs the oracle."""
+    """Per-node parity with IDENTICAL inputs (SURVEY.md section 8c methodology): every non-Const node of
+    the graph is run through our plugin on the oracle's own input feature maps and compared with the
+    oracle's output for that node."""
     from oracle import ref_engine
+    from pyopenvino_b200.inference_engine import IECore
     from tools.synth_bin import synth_input
     x = synth_input(model, batch=1, seed=1)
     oracle = ref_engine.load(os.path.join(model_dir, model + '.xml'), 'special')
     oracle.infer({oracle.net.inputs[0]['name']: x})
-    want = oracle.node_outputs()
-    net, exe = _load(model_dir, model, fuse=False, use_graph=False)
-    exe.infer({net.inputs[0]['name']: x})
+    plugins = IECore().plugins.plugins
     checked = 0
-    for nid in net.G.nodes:
-        n = net.G.nodes[nid]
-        if 'output' not in n or n['type'] == 'Const':
+    exact = {'MaxPool', 'ReLU', 'Add', 'Multiply', 'Clamp', 'Concat', 'Reshape', 'Transpose'}
+    for nid in oracle.net.order:
+        rn = oracle.net.nodes[nid]
+        if rn['type'] in ('Const', 'Parameter', 'Result'):
             continue
-        p = next(iter(n['output']))
-        got = np.asarray(n['output'][p]['data'])
-        ok, msg = close(got, want[n['name']], rtol=1e-4, atol=1e-5)
-        assert ok, (n['name'], n['type'], msg)
+        ins = {tp: oracle.net.nodes[fl]['output'][fp]['data'] for fl, fp, tp in oracle.net.pred[nid]}
+        port = next(iter(rn['output']))
+        node = {'name': rn['name'], 'type': rn['type'], 'data': dict(rn.get('data', {})), 'input': rn['input'],
+                'output': {port: {'precision': rn['output'][port]['precision'], 'dims': rn['output'][port]['dims']}}}
+        got = np.asarray(plugins[rn['type']].compute(node, ins, kernel_type='numpy')[port])
+        want = rn['output'][port]['data']
+        if rn['type'] in exact:
+            assert np.array_equal(got, want), (rn['name'], rn['type'])
+        else:
+            ok, msg = close(got, want, rtol=1e-4, atol=1e-5)
+            assert ok, (rn['name'], rn['type'], msg)
         checked += 1
     assert checked > 20
+
+
+@pytest.mark.parametrize('model', ['mnist_bn', 'googlenet-v1'])
+def test_unfused_eager_end_to_end_vs_oracle(model_dir, model):
+    """The reference-like mode (every node through its plugin, outputs materialised) end to end."""
+    from oracle import ref_engine
+    from tools.synth_bin import synth_input
+    x = synth_input(model, batch=1, seed=1)
+    oracle = ref_engine.load(os.path.join(model_dir, model + '.xml'), 'special')
+    want = next(iter(oracle.infer({oracle.net.inputs[0]['name']: x}).values()))
+    net, exe = _load(model_dir, model, fuse=False, use_graph=False)
+    got = exe.infer({net.inputs[0]['name']: x})[net.outputs[0]['name']]
+    ok, msg = close(got, want, rtol=1e-4, atol=1e-6)
+    assert ok, msg
+    assert np.argmax(got) == np.argmax(want)
+    # every node output is materialised on the graph like in the reference (inference_engine.py:290-292)
+    for nid in net.G.nodes:
+        n = net.G.nodes[nid]
+        if 'output' in n:
+            assert 'data' in n['output'][next(iter(n['output']))], n['name']
 
 
 def test_batch_is_stack_of_batch1(model_dir):
