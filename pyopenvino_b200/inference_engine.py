@@ -245,6 +245,8 @@ class Executable_Network:
         self._static_out = {}
         self._user_inputs = {}
         self._graph_launches = 0
+        self._step_events = None
+        self._weights = None
         self.last_node_seconds = {}
 
     # ---- scheduling (inference_engine.py:218-242) -------------------------------------------------
@@ -476,10 +478,18 @@ class Executable_Network:
                     host_inputs = {k: (np.asarray(v) if is_device(v) else v) for k, v in inputs.items()}
                     pickle.dump(({k: v for k, v in node.items() if k not in ('output', 'const')}, host_inputs), file=f)
             stime = time.time()
+            ev = None
+            if self._step_events is not None and node_type != 'Const':
+                import torch
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             if fused:
                 res = p.plugins[node_type].compute(node, inputs, kernel_type=self.kernel_type, debug=False, fused=fused)
             else:
                 res = p.plugins[node_type].compute(node, inputs, kernel_type=self.kernel_type, debug=False)
+            if ev is not None:
+                ev[1].record()
+                self._step_events.append((task, ev[0], ev[1]))
             if verbose:
                 import torch
                 torch.cuda.current_stream().synchronize()
@@ -556,6 +566,7 @@ class Executable_Network:
         from . import device as dev
         from .device import DeviceArray
         G = self.ienet.G
+        self.load_constants()
         # static input staging: pinned host + device buffers
         self._static_in = {}
         for node in self._param_nodes():
@@ -641,6 +652,81 @@ class Executable_Network:
         self.stage_inputs(self._user_inputs)
         self.replay()
         return self.fetch_outputs()
+
+    def load_constants(self):
+        """Upload every float Const into ONE resident HBM buffer (the weight arena) with a single H2D copy;
+        each Const node's DeviceArray is a view into it.  Returns the flat torch tensor (what
+        `distributed.broadcast_weights` sends from rank 0)."""
+        import torch
+        from .device import DeviceArray
+        dev = self._ensure_device()
+        if self._weights is not None:
+            return self._weights
+        G = self.ienet.G
+        items, total = [], 0
+        for node_id, _ in self.ienet.find_node_by_type('Const'):
+            node = G.nodes[node_id]
+            if common_def.type_convert_tbl[node['data']['element_type']] is not np.float32:
+                continue
+            n = int(node['const']['data'].size)
+            items.append((node, total, n))
+            total += (n + 63) // 64 * 64
+        host = torch.zeros(max(total, 1), dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for node, off, n in items:
+            hv[off:off + n] = node['const']['data']
+        with torch.cuda.stream(self.stream):
+            flat = torch.empty(max(total, 1), dtype=torch.float32, device='cuda')
+            flat.copy_(host, non_blocking=True)
+            self.stream.synchronize()
+        for node, off, n in items:
+            arr = DeviceArray(flat[off:off + max(n, 1)], node['data']['shape'], 'plain')
+            if n <= 4096:
+                arr.cache['host'] = np.array(node['const']['data'], dtype=np.float32).reshape(node['data']['shape'])
+            node['const']['device'] = arr
+        self._weights = flat
+        return flat
+
+    def profile_steps(self, inputs: dict, iters: int = 3):
+        """Per-step device time of the fused plan run eagerly (CUDA events around every plugin call on
+        self.stream).  Returns [{'id', 'type', 'name', 'ms'}] averaged over `iters` passes."""
+        import torch
+        from . import device as dev
+        self._ensure_device()
+        if self._plan is None:
+            self.build_plan()
+        G = self.ienet.G
+        self._user_inputs = dict(inputs)
+        acc = {}
+        with torch.cuda.stream(self.stream):
+            if self.use_graph:
+                if self._graph is None:
+                    self._prepare_graph()
+                self.stage_inputs(inputs)
+            else:
+                for name, val in inputs.items():
+                    for node in G.nodes:
+                        if G.nodes[node]['name'] == name:
+                            G.nodes[node]['param'] = val
+            arena = self._arena if self._arena is not None else dev.Arena()
+            frozen = arena.frozen
+            arena.frozen = False
+            dev.set_arena(arena)
+            try:
+                for it in range(iters + 1):
+                    arena.reset()
+                    self._step_events = []
+                    self._run(capture=self.use_graph)
+                    self.stream.synchronize()
+                    if it > 0:
+                        for task, e0, e1 in self._step_events:
+                            acc[task] = acc.get(task, 0.0) + e0.elapsed_time(e1)
+                    self._step_events = None
+            finally:
+                dev.set_arena(None)
+                arena.frozen = frozen
+                self._step_events = None
+        return [{'id': t, 'type': G.nodes[t]['type'], 'name': G.nodes[t]['name'], 'ms': ms / iters} for t, ms in acc.items()]
 
     def kernels_per_inference(self):
         """Number of libb200ov kernel launches captured in the graph (0 before the first inference)."""
