@@ -12,8 +12,10 @@
  *     consecutive pixels, ld >= C).  ld > C lets a producer write straight into a channel slice
  *     of a Concat buffer.  The logical (IR) shape stays NCHW; the Python host tracks the tag.
  *   - 2-D tensors (MatMul operands, SoftMax rows): row-major.
- *   - conv weights: packed once per network by b200ov_pack_conv_weights() to
- *     [K = kh*kw*cin rows (padded to a multiple of 16)][ldw = cout padded to a multiple of 64].
+ *   - conv weights: packed once per network by b200ov_pack_conv_weights() into one buffer with two
+ *     sections: (1) FP32 section [K = kh*kw*cin rows (padded to 16)][ldw = cout padded to 64] for the
+ *     CUDA-core kernel; (2) when cin % 4 == 0 and cin >= 8, the tcgen05 section: tf32 hi and lo planes,
+ *     each [cout padded to 32][kh*kw*(cin padded to 32)] K-major, read by TMA.
  *
  * Each function cites the reference interface it replaces (paths relative to the
  * yas-sim/pyopenvino root).
@@ -95,8 +97,8 @@ typedef struct {
 } b200ov_conv_desc;
 
 /* OIHW -> packed [kh*kw*cin (pad 16)][ldw] (row index ordered ky, kx, ci).  `ldw` and the row
- * count come from b200ov_conv_weight_dims().  Replaces `kernel.reshape(kn,-1).T`, Convolution.py:83. */
-int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* ldw);
+ * count come from b200ov_conv_weight_dims(); `w_packed` must hold `total_floats`.  Replaces `kernel.reshape(kn,-1).T`, Convolution.py:83. */
+int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* ldw, int64_t* total_floats);
 int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int cin, int kh, int kw, void* stream);
 
 /* y = act(conv(x, w) + bias).  Replaces Convolution.compute (Convolution.py:149-176) and, through

@@ -56,7 +56,7 @@ SIGNATURES = {
     'b200ov_graph_end': [_P, C.POINTER(_P)],
     'b200ov_graph_launch': [_P, _P],
     'b200ov_graph_destroy': [_P],
-    'b200ov_conv_weight_dims': [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)],
+    'b200ov_conv_weight_dims': [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)],
     'b200ov_pack_conv_weights': [_P, _P, _I, _I, _I, _I, _P],
     'b200ov_conv2d': [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
     'b200ov_matmul': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P],

@@ -24,6 +24,11 @@ static int validate(const b200ov_conv_desc* d, const float* x, const float* wp, 
   return B200OV_OK;
 }
 
+// the tf32 section follows the FP32 section inside the packed weight buffer
+static const float* tf32_section(const b200ov_conv_desc* d, const float* w_packed) {
+  return w_packed + (long long)round_up(d->kh * d->kw * d->cin, 16) * d->ldw;
+}
+
 extern "C" {
 
 int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias, float* y,
@@ -36,12 +41,12 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
       return conv2d_ffma(d, x, w_packed, bias, y, s);
     case B200OV_MATH_TF32X3:
     case B200OV_MATH_TF32:
-      return conv2d_tcgen05(d, x, w_packed, bias, y, s, false);
+      return conv2d_tcgen05(d, x, tf32_section(d, w_packed), bias, y, s, false);
     case B200OV_MATH_AUTO: {
-      if (conv2d_tcgen05(d, x, w_packed, bias, y, s, true) == B200OV_OK) {
+      if (conv2d_tcgen05(d, x, nullptr, bias, y, s, true) == B200OV_OK) {
         b200ov_conv_desc dd = *d;
         dd.math = B200OV_MATH_TF32X3;
-        return conv2d_tcgen05(&dd, x, w_packed, bias, y, s, false);
+        return conv2d_tcgen05(&dd, x, tf32_section(d, w_packed), bias, y, s, false);
       }
       return conv2d_ffma(d, x, w_packed, bias, y, s);
     }

@@ -257,26 +257,44 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
 
 }  // namespace b200ov
 
+namespace b200ov {
+void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* kpad);
+int pack_tf32_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s);
+static bool has_tf32_section(int cin) { return cin % 4 == 0 && cin >= 8; }
+}  // namespace b200ov
+
 using namespace b200ov;
 
 extern "C" {
 
-int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* ldw) {
+int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* ldw, int64_t* total_floats) {
   B200OV_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0, "bad filter dims");
-  if (rows) *rows = round_up(kh * kw * cin, 16);
-  if (ldw) *ldw = round_up(cout, 64);
+  const int r = round_up(kh * kw * cin, 16), l = round_up(cout, 64);
+  if (rows) *rows = r;
+  if (ldw) *ldw = l;
+  if (total_floats) {
+    long long total = (long long)r * l;
+    if (has_tf32_section(cin)) {
+      int coutp;
+      long long kpad;
+      tf32_weight_dims(cout, cin, kh, kw, &coutp, &kpad);
+      total += 2LL * coutp * kpad;
+    }
+    *total_floats = total;
+  }
   return B200OV_OK;
 }
 
 int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int cin, int kh, int kw, void* stream) {
   B200OV_REQUIRE(w_oihw && w_packed, "null weight pointer");
   int rows, ldw;
-  int rc = b200ov_conv_weight_dims(cout, cin, kh, kw, &rows, &ldw);
+  int rc = b200ov_conv_weight_dims(cout, cin, kh, kw, &rows, &ldw, nullptr);
   if (rc) return rc;
   long long total = (long long)rows * ldw;
   pack_conv_weights_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_oihw, w_packed, cout, cin, kh, kw,
                                                                               kh * kw * cin, rows, ldw);
   B200OV_LAUNCH_CHECK("pack_conv_weights_kernel");
+  if (has_tf32_section(cin)) return pack_tf32_weights(w_oihw, w_packed + total, cout, cin, kh, kw, as_stream(stream));
   return B200OV_OK;
 }
 

@@ -160,11 +160,11 @@ def pack_conv(w):
     else:
         cout, cin = w.shape
         kh = kw = 1
-    rows, ldw = C.c_int(0), C.c_int(0)
-    _cabi.call('b200ov_conv_weight_dims', cout, cin, kh, kw, C.byref(rows), C.byref(ldw))
+    rows, ldw, total = C.c_int(0), C.c_int(0), C.c_int64(0)
+    _cabi.call('b200ov_conv_weight_dims', cout, cin, kh, kw, C.byref(rows), C.byref(ldw), C.byref(total))
     pk = PackedWeights()
     # packed weights are long-lived: never from the per-inference arena
-    pk.t = torch.empty(rows.value * ldw.value, dtype=torch.float32, device='cuda')
+    pk.t = torch.empty(total.value, dtype=torch.float32, device='cuda')
     pk.rows, pk.ldw, pk.cout, pk.cin, pk.kh, pk.kw = rows.value, ldw.value, cout, cin, kh, kw
     _cabi.call('b200ov_pack_conv_weights', _p(w), C.c_void_p(pk.ptr), cout, cin, kh, kw, _s())
     w.cache['conv'] = pk

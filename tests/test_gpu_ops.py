@@ -52,15 +52,29 @@ def test_plugin_vs_reference_vectors(i, plugins):
         assert ok, (m['tag'], msg)
 
 
-@pytest.mark.parametrize('kt', ['fp32'])
+@pytest.mark.parametrize('kt', ['fp32', 'tf32x3', 'tf32'])
 def test_conv_math_modes(kt, plugins):
+    """'fp32' = CUDA-core FFMA, 'tf32x3' = tcgen05 hi/lo split (both must meet the FP32 tolerance),
+    'tf32' = single-pass tcgen05: only the relaxed 1e-3 class, checked relative to the tensor scale."""
+    from pyopenvino_b200 import _cabi
+    ran = 0
     for i, m in enumerate(META):
         if m['type'] != 'Convolution':
             continue
         node, ins, op = _node(i, m)
-        got = np.asarray(plugins['Convolution'].compute(node, dict(ins), kernel_type=kt)[op])
-        ok, msg = close(got, OPS['c{}_out_numpy'.format(i)])
-        assert ok, (m['tag'], kt, msg)
+        want = OPS['c{}_out_numpy'.format(i)]
+        try:
+            got = np.asarray(plugins['Convolution'].compute(node, dict(ins), kernel_type=kt)[op])
+        except _cabi.B200ovError as e:
+            assert kt != 'fp32' and 'tcgen05 path needs' in str(e), str(e)      # C_in = 1 / 3 stems are FFMA-only
+            continue
+        ran += 1
+        if kt == 'tf32':
+            assert np.abs(got - want).max() <= 2e-3 * max(1.0, np.abs(want).max()), m['tag']
+        else:
+            ok, msg = close(got, want)
+            assert ok, (m['tag'], kt, msg)
+    assert ran >= 5
 
 
 def test_conv_pickle_known_answer(plugins):
