@@ -179,6 +179,24 @@ int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, i
 /* rows x cols strided copy (Concat.py:9-13 when producers could not write in place). */
 int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream);
 
+/* ---- SSD DetectionOutput ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n;                          /* images                                                       */
+  int32_t num_priors, num_classes;    /* 1917, 91 for ssd_mobilenet_v1_coco                            */
+  int32_t keep_top_k;                 /* records per image                                            */
+  int32_t code_center_size;           /* 1 = caffe.PriorBoxParameter.CENTER_SIZE, 0 = CORNER          */
+  int32_t variance_encoded_in_target;
+  int32_t clip_before_nms, clip_after_nms;
+  float confidence_threshold, nms_threshold;
+} b200ov_detection_desc;
+/* Replaces DetectionOutput.compute (DetectionOutput.py:162-300) for share_location / normalized priors:
+ * top-1 class per prior, threshold, box decode, class-agnostic all-pairs NMS, score-ordered records
+ * [rank, class, score, xmin, ymin, xmax, ymax] with a [-1,0,..] terminator.  loc [n][priors*4],
+ * conf [n][priors*classes], proposals [2][priors*4] (boxes, variances), out [n*keep_top_k][7].
+ * Decisions and record order are bit-compatible with the reference's float32 python arithmetic. */
+int b200ov_detection_output(const b200ov_detection_desc* d, const float* loc, const float* conf,
+                            const float* proposals, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

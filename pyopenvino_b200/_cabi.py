@@ -35,6 +35,12 @@ class PoolDesc(C.Structure):
                                          'x_ld', 'y_ld', 'mode')]
 
 
+class DetectionDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('n', 'num_priors', 'num_classes', 'keep_top_k', 'code_center_size',
+                                         'variance_encoded_in_target', 'clip_before_nms', 'clip_after_nms')] + \
+               [('confidence_threshold', C.c_float), ('nms_threshold', C.c_float)]
+
+
 _P, _I, _F, _L, _Z = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
 # name -> argtypes; every function returns int except the two noted below
@@ -70,6 +76,7 @@ SIGNATURES = {
     'b200ov_transpose': [_P, _P, _I, _I, _I, _I, _I, _P],
     'b200ov_nchw_to_nhwc_affine': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _F, _P],
     'b200ov_copy2d': [_P, _P, _L, _I, _I, _I, _P],
+    'b200ov_detection_output': [C.POINTER(DetectionDesc), _P, _P, _P, _P, _P],
 }
 NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
 
@@ -78,7 +85,7 @@ launch_count = 0          # kernels launched through this binding (bench.py repo
 
 _LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_matmul', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
               'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_transpose',
-              'b200ov_nchw_to_nhwc_affine', 'b200ov_copy2d'}
+              'b200ov_nchw_to_nhwc_affine', 'b200ov_copy2d', 'b200ov_detection_output'}
 
 
 def load():

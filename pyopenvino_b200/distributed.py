@@ -58,9 +58,13 @@ def gather_outputs(local, sizes=None):
         out = torch.empty((size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous())
         return out
-    parts = [torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for n in sizes]
-    dist.all_gather(parts, local.contiguous())
-    return torch.cat(parts, dim=0)
+    # uneven shards: pad every rank's rows to the largest shard, gather, drop the padding
+    rows = max(sizes)
+    padded = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((size * rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * rows:r * rows + n] for r, n in enumerate(sizes)], dim=0)
 
 
 def max_over_ranks(value):

@@ -349,3 +349,19 @@ def channel_slice(buf, c_off, c):
     n, ct, h, w = buf.shape
     assert buf.layout == 'nhwc' and c_off + c <= ct
     return DeviceArray(buf.t, (n, c, h, w), 'nhwc', ld=buf.ld, c_off=buf.c_off + c_off)
+
+
+def detection_output(loc, conf, proposals, num_classes, keep_top_k, center_size, variance_in_target, clip_before, clip_after,
+                     conf_thr, nms_thr):
+    """SSD post-process for a batch: loc [N, P*4], conf [N, P*classes], proposals [1, 2, P*4] -> [1, 1, N*keep, 7]."""
+    loc, conf, proposals = as_plain(loc), as_plain(conf), as_plain(proposals)
+    n = loc.shape[0]
+    priors = proposals.shape[2] // 4
+    assert loc.size == n * priors * 4 and conf.size == n * priors * num_classes
+    out = DeviceArray(dev.alloc_f32(n * keep_top_k * 7), (1, 1, n * keep_top_k, 7), 'plain')
+    d = _cabi.DetectionDesc(n=n, num_priors=priors, num_classes=num_classes, keep_top_k=keep_top_k,
+                            code_center_size=int(center_size), variance_encoded_in_target=int(variance_in_target),
+                            clip_before_nms=int(clip_before), clip_after_nms=int(clip_after),
+                            confidence_threshold=conf_thr, nms_threshold=nms_thr)
+    _cabi.call('b200ov_detection_output', C.byref(d), _p(loc), _p(conf), _p(proposals), _p(out), _s())
+    return out

@@ -74,7 +74,7 @@ def test_synthetic_models_vs_reference_golden(model_dir, model):
         assert np.argmax(res[img]) == np.argmax(want)
 
 
-@pytest.mark.parametrize('model', ['mnist_bn', 'googlenet-v1'])
+@pytest.mark.parametrize('model', ['mnist_bn', 'googlenet-v1', 'ssd_mobilenet_v1_coco'])
 def test_every_node_vs_oracle(model_dir, model):
     """Per-node parity with IDENTICAL inputs (SURVEY.md section 8c methodology): every non-Const node of
     the graph is run through our plugin on the oracle's own input feature maps and compared with the
@@ -87,7 +87,8 @@ def test_every_node_vs_oracle(model_dir, model):
     oracle.infer({oracle.net.inputs[0]['name']: x})
     plugins = IECore().plugins.plugins
     checked = 0
-    exact = {'MaxPool', 'ReLU', 'Add', 'Multiply', 'Clamp', 'Concat', 'Reshape', 'Transpose'}
+    exact = {'MaxPool', 'ReLU', 'Add', 'Multiply', 'Clamp', 'Concat', 'Reshape', 'Transpose', 'GroupConvolution', 'Unsqueeze',
+             'ShapeOf', 'StridedSlice', 'PriorBoxClustered', 'DetectionOutput'}
     for nid in oracle.net.order:
         rn = oracle.net.nodes[nid]
         if rn['type'] in ('Const', 'Parameter', 'Result'):
@@ -152,3 +153,30 @@ def test_fused_graph_equals_unfused_eager(model_dir):
     ok, msg = close(a, c, rtol=1e-5, atol=1e-7)
     assert ok, msg
     assert exe.kernels_per_inference() > 0
+
+
+def _records(block):
+    """Valid records of one image's (keep_top_k, 7) block (up to the -1 terminator)."""
+    stop = np.where(block[:, 0] == -1)[0]
+    return block[:int(stop[0])] if len(stop) else block
+
+
+@pytest.mark.parametrize('fuse,use_graph', [(True, True), (False, False)])
+def test_ssd_end_to_end_vs_reference_golden(model_dir, fuse, use_graph):
+    """SSD-MobileNet-v1 (synthetic weights) batch 2: box ORDER and class ids identical to the reference's
+    own run, scores / coordinates within the FP32 tolerance."""
+    from tools.synth_bin import synth_input
+    g = np.load(os.path.join(GOLDEN, 'models_e2e.npz'))
+    model = 'ssd_mobilenet_v1_coco'
+    x = synth_input(model, batch=2, seed=1)
+    net, exe = _load(model_dir, model, batch=2, fuse=fuse, use_graph=use_graph)
+    res = exe.infer({net.inputs[0]['name']: x})[net.outputs[0]['name']]
+    assert res.shape == (1, 1, 200, 7)
+    for img in range(2):
+        want = _records(g['{}|special|{}|final'.format(model, img)][0, 0])
+        got = _records(res[0, 0, img * 100:(img + 1) * 100])
+        assert len(want) > 5
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.array_equal(got[:, 0:2], want[:, 0:2])          # rank + class id, in order
+        ok, msg = close(got[:, 2:], want[:, 2:], rtol=1e-4, atol=1e-5)
+        assert ok, msg
