@@ -318,6 +318,8 @@ def main():
                                               'Const rebuilt per inference, host_cpus={}'.format(n, dt, os.cpu_count())}
         print(json.dumps(line), flush=True)
     distributed.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
