@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         src, obj, stale = job
         if not stale:
             return ''
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('B200OV_EXTRA_NVCC_FLAGS', '').split() + ['-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for {}:\n{}\n{}'.format(src, r.stdout, r.stderr))

@@ -33,6 +33,14 @@ namespace b200ov {
 
 namespace tc {
 
+#ifdef B200OV_TC_TRACE
+// developer-only pipeline trace (build with B200OV_EXTRA_NVCC_FLAGS=-DB200OV_TC_TRACE): clock64 per role / K block
+__device__ unsigned long long g_trace[8][128];
+#define TC_TRACE(ev, idx) do { if (blockIdx.x == gridDim.x / 2 && (idx) < 128) g_trace[ev][idx] = clock64(); } while (0)
+#else
+#define TC_TRACE(ev, idx) do { } while (0)
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                         // 32 floats = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
@@ -199,47 +207,70 @@ conv_tcgen05_kernel(const Params p, const float* __restrict__ x, const float* __
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (tid == 0) TC_TRACE(7, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_smem;
+  if (tid == 0) TC_TRACE(7, 1);
 
   if (warp < 4) {
     // ================= producers: im2col gather of A (cp.async) + TMA of the weight tiles =============
-    const int row = tid;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    const int mm = row_ok ? m : 0;
-    const int img = mm / p.ohow;
-    const int r = mm - img * p.ohow;
-    const int oy = r / p.ow, ox = r - oy * p.ow;
-    const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
-    const float* ximg = x + (long long)img * p.h * p.w * p.x_ld;
-    const uint32_t row_off = row * 128;
-    const uint32_t sw = row & 7;
-    int tap = 0, cb = 0;
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(bar_empty(s), ph ^ 1);
-      const int ky = tap / p.kw, kx = tap - ky * p.kw;
-      const int iy = iy0 + ky, ix = ix0 + kx;
-      const bool inb = row_ok && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-      const int ci0 = cb * BLOCK_K;
-      const float* src = inb ? ximg + ((long long)iy * p.w + ix) * p.x_ld + ci0 : x;
-      const uint32_t dst = base + L::A_HI + s * A_TILE_BYTES + row_off;
+    // Thread t copies 16-byte chunk (t & 7) of rows (t >> 3) + 16*i, i = 0..7: eight neighbouring threads
+    // fetch one pixel's whole 128-byte channel run, so every LDGSTS warp instruction moves 4 full lines
+    // (one shared-memory wavefront per line instead of one per thread).
+    const int chunk = tid & 7;
+    int iy0[8], ix0[8];
+    long long img_off[8];
+    uint32_t dst_off[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const bool v = inb && (ci0 + c * 4 < p.cin);
-        cp_async_16(dst + ((c ^ sw) << 4), v ? src + c * 4 : x, v ? 16u : 0u);
+    for (int i = 0; i < 8; ++i) {
+      const int row = (tid >> 3) + 16 * i;
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const int mm = row_ok ? m : 0;
+      const int img = mm / p.ohow;
+      const int r = mm - img * p.ohow;
+      const int oy = r / p.ow, ox = r - oy * p.ow;
+      iy0[i] = row_ok ? oy * p.sh - p.pt : -(1 << 28);       // an invalid row never passes the bounds test
+      ix0[i] = ox * p.sw - p.pl;
+      img_off[i] = (long long)img * p.h * p.w * p.x_ld;
+      dst_off[i] = row * 128 + ((chunk ^ (row & 7)) << 4);
+    }
+    int kb = 0;
+    const int taps = p.kh * p.kw;
+    for (int tap = 0; tap < taps; ++tap) {
+      // per tap: source pointer and validity of each of this thread's 8 rows (hoisted out of the channel loop)
+      const int ky = tap / p.kw, kx = tap - ky * p.kw;
+      const float* src[8];
+      uint32_t valid = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+        const bool v = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        valid |= (v ? 1u : 0u) << i;
+        src[i] = x + (v ? img_off[i] + ((long long)iy * p.w + ix) * p.x_ld + chunk * 4 : 0);
       }
-      cp_async_mbar_arrive_noinc(bar_a_full(s));
-      if (tid == 0) {
-        mbar_arrive_expect_tx(bar_b_full(s), X3 ? 2 * L::B_TILE_BYTES : L::B_TILE_BYTES);
-        tma_load_2d(base + L::B_HI + s * L::B_TILE_BYTES, &map_hi, kb * BLOCK_K, n0, bar_b_full(s));
-        if (X3) tma_load_2d(base + L::B_LO + s * L::B_TILE_BYTES, &map_lo, kb * BLOCK_K, n0, bar_b_full(s));
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        if (tid == 0) TC_TRACE(0, kb);
+        const uint32_t ok_mask = (cb * BLOCK_K + chunk * 4 < p.cin) ? valid : 0u;
+        const uint32_t dst = base + L::A_HI + s * A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool v = (ok_mask >> i) & 1u;
+          cp_async_16(dst + dst_off[i], v ? src[i] + cb * BLOCK_K : x, v ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(bar_a_full(s));
+        if (tid == 0) TC_TRACE(1, kb);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar_b_full(s), X3 ? 2 * L::B_TILE_BYTES : L::B_TILE_BYTES);
+          tma_load_2d(base + L::B_HI + s * L::B_TILE_BYTES, &map_hi, kb * BLOCK_K, n0, bar_b_full(s));
+          if (X3) tma_load_2d(base + L::B_LO + s * L::B_TILE_BYTES, &map_lo, kb * BLOCK_K, n0, bar_b_full(s));
+        }
       }
-      if (++cb == p.cin_blocks) { cb = 0; ++tap; }
     }
   } else if (warp < 8) {
     // ================= converters: FP32 -> tf32 hi / lo split of the A tile =============================
@@ -269,24 +300,31 @@ conv_tcgen05_kernel(const Params p, const float* __restrict__ x, const float* __
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(bar_a_full(s), ph);
+      if (c == 0) TC_TRACE(2, kb);
       float4* a_hi = reinterpret_cast<float4*>(base_ptr + L::A_HI + s * A_TILE_BYTES);
       float4* a_lo = reinterpret_cast<float4*>(base_ptr + L::A_LO + s * A_TILE_BYTES);
 #pragma unroll
       for (int i = 0; i < A_TILE_BYTES / 16 / NUM_CONVERTERS; ++i) {
         const int idx = i * NUM_CONVERTERS + c;
         float4 v = a_hi[idx];
-        uint32_t h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
-        a_hi[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
         if (X3) {
-          uint32_t l0 = to_tf32(v.x - __uint_as_float(h0)), l1 = to_tf32(v.y - __uint_as_float(h1));
-          uint32_t l2 = to_tf32(v.z - __uint_as_float(h2)), l3 = to_tf32(v.w - __uint_as_float(h3));
-          a_lo[idx] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          // hi = the top 19 bits (exact tf32), lo = v - hi (exact in FP32; the tensor core keeps its top 19 bits):
+          // v = hi + lo + O(2^-20 |v|), two ALU ops per element
+          const float h0 = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          const float h2 = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          a_hi[idx] = make_float4(h0, h1, h2, h3);
+          a_lo[idx] = make_float4(v.x - h0, v.y - h1, v.z - h2, v.w - h3);
+        } else {
+          uint32_t h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
+          a_hi[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
         }
       }
       fence_proxy_async();
       mbar_arrive(bar_conv(s));
+      if (c == 0) TC_TRACE(3, kb);
       // the MMA warp runs at most STAGES blocks behind us: chunk (current - 2) retired long ago
       if (kb % CHUNK == 0 && kb / CHUNK >= 2) promote(kb / CHUNK - 2);
+      if (c == 0) TC_TRACE(4, kb);
     }
     // ================= epilogue: remaining chunks + cross terms -> (+bias, act) -> NHWC global ==========
     if (num_chunks >= 2) promote(num_chunks - 2);
@@ -300,6 +338,7 @@ conv_tcgen05_kernel(const Params p, const float* __restrict__ x, const float* __
         for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(v[j]);
       }
     }
+    if (c == 0) TC_TRACE(7, 2);
     const int m = m0 + ew * 32 + lane;
     const bool vec_ok = ((p.y_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
 #pragma unroll
@@ -337,10 +376,14 @@ conv_tcgen05_kernel(const Params p, const float* __restrict__ x, const float* __
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       const int chunk = kb / CHUNK, buf = chunk & 1;
+      if (lane == 0) TC_TRACE(0, 64 + kb);
       if (kb % CHUNK == 0) mbar_wait(bar_acc_free(buf), ((chunk >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+      if (lane == 0) TC_TRACE(1, 64 + kb);
       mbar_wait(bar_conv(s), ph);
+      if (lane == 0) TC_TRACE(2, 64 + kb);
       mbar_wait(bar_b_full(s), ph);
       tc_fence_after();
+      if (lane == 0) TC_TRACE(5, kb);
       if (lane == 0) {
         const uint64_t a_hi = make_smem_desc(base + L::A_HI + s * A_TILE_BYTES);
         const uint64_t a_lo = make_smem_desc(base + L::A_LO + s * A_TILE_BYTES);
@@ -358,11 +401,13 @@ conv_tcgen05_kernel(const Params p, const float* __restrict__ x, const float* __
         }
         umma_commit(bar_empty(s));                               // frees the stage when these MMAs retire
         if (kb % CHUNK == CHUNK - 1 || kb == p.num_k_blocks - 1) umma_commit(bar_chunk_done(buf));
+        TC_TRACE(6, kb);
       }
       __syncwarp();
     }
   }
 
+  if (tid == NUM_PRODUCERS) TC_TRACE(7, 3);
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
@@ -387,7 +432,7 @@ __global__ void pack_tf32_weights_kernel(const float* __restrict__ w, float* __r
     }
     uint32_t hi, lo;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+    lo = __float_as_uint(v - __uint_as_float(hi));     // exact residual; the tensor core keeps its top 19 bits
     out[idx] = __uint_as_float(hi);
     out[plane + idx] = __uint_as_float(lo);
   }
@@ -442,6 +487,12 @@ static int launch(const Params& p, const float* x, const float* bias, float* y, 
 }
 
 }  // namespace tc
+
+#ifdef B200OV_TC_TRACE
+extern "C" int b200ov_debug_trace(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, tc::g_trace, sizeof(tc::g_trace)) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 bool tcgen05_eligible(const b200ov_conv_desc* d, const float* x) {
   return (d->cin % 4 == 0) && (d->x_ld % 4 == 0) && aligned16(x) && d->cin >= 8;
