@@ -121,13 +121,20 @@ typedef struct {
   int32_t x_ld, y_ld;
   int32_t act;
   float act_lo, act_hi;
+  int32_t math;                /* B200OV_DW_*                                                    */
 } b200ov_dwconv_desc;
+
+enum {
+  B200OV_DW_AUTO = 0,   /* 3x3: packed-FP32 FMA chain from the bias (a few ulp from the reference)          */
+  B200OV_DW_EXACT = 1   /* products rounded individually, numpy pairwise order: bit-identical to np.sum() */
+};
 
 /* [C][1][1][kh][kw] -> [kh*kw][C] */
 int b200ov_pack_dw_weights(const float* w_g11hw, float* w_packed, int c, int kh, int kw, void* stream);
 /* Replaces GroupConvolution.compute (GroupConvolution.py:114-137, depthwise case) + Add + Clamp.
- * Products are summed in numpy's pairwise order without FMA contraction, so the pre-bias value is
- * bit-identical to `np.sum(patch*flt)` (GroupConvolution.py:78). */
+ * math = B200OV_DW_EXACT: products are summed in numpy's pairwise order without FMA contraction, so the
+ * pre-bias value is bit-identical to `np.sum(patch*flt)` (GroupConvolution.py:78); B200OV_DW_AUTO may use
+ * an FMA chain (3x3 windows), which meets the FP32 tolerance class but is not bit-identical. */
 int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_packed, const float* bias,
                     float* y, void* stream);
 

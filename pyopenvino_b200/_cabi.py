@@ -27,7 +27,11 @@ class ConvDesc(C.Structure):
 
 class DwConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
-                                         'x_ld', 'y_ld', 'act')] + [('act_lo', C.c_float), ('act_hi', C.c_float)]
+                                         'x_ld', 'y_ld', 'act')] + [('act_lo', C.c_float), ('act_hi', C.c_float),
+                                                                    ('math', C.c_int32)]
+
+
+DW_AUTO, DW_EXACT = 0, 1
 
 
 class PoolDesc(C.Structure):

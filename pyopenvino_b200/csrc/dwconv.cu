@@ -1,17 +1,22 @@
 // Depthwise GroupConvolution (NHWC) with fused bias + activation.
 //
 // Reference: GroupConvolution.py:53-79, `out[g,oy,ox] = np.sum(in_pad[g, window] * w[g,0,0])`.
-// Bandwidth-bound (0.9-2.2 FLOP/B): one thread owns V consecutive channels of one output pixel,
-// so a warp reads/writes 32*V consecutive floats of the NHWC row (128-bit accesses for V = 4).
-// The kh*kw products are rounded individually (no FMA contraction) and summed in the order numpy's
-// pairwise float32 reduction uses, so the pre-bias value is bit-identical to the reference.
+// Bandwidth-bound (0.9-2.2 FLOP/B).  The 3x3 hot case uses a register-blocked strip kernel (below): the naive
+// one-thread-per-output form issues 9 loads per output and is limited by the LSU / L1 wavefront rate, not HBM.
+// Index arithmetic is 32-bit with multiply-high division (fastdiv.cuh).
+// The generic kernel rounds the kh*kw products individually (no FMA contraction) and sums them in the order
+// numpy's pairwise float32 reduction uses, so its pre-bias value is bit-identical to the reference.
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b200ov {
 
 struct DwP {
   int n, h, w, c, kh, kw, sh, sw, pt, pl, oh, ow, x_ld, y_ld, act;
   float lo, hi;
+  int owt;                 // output column tiles per row = ceil(ow / TW)
+  uint32_t total;          // work items
+  FastDiv d_cg, d_owt, d_oh;
 };
 
 template <int V> struct Vec;
@@ -26,6 +31,138 @@ template <> struct Vec<1> {
   __device__ void store(float* p) const { *p = v[0]; }
 };
 
+// ---- 3x3 hot path ------------------------------------------------------------------------------------
+struct DwStripP {
+  int h, w, c, pt, pl, oh, ow, x_ld, y_ld, act, th;
+  float lo, hi;
+  uint32_t total;                // work items = n * strips * ceil(ow / 2) * (c / 4)
+  FastDiv d_cg, d_owt, d_strips;
+};
+
+// Packed FP32 pairs (sm_100 FFMA2): two fused multiply-adds per instruction.  This fast path accumulates
+// the nine taps as an FMA chain starting from the bias, so it agrees with the reference's
+// np.sum(patch * flt) + bias to a few ulp (tolerance class 1e-5 + 1e-4|ref|), not bit for bit; ptxas
+// contracts mul.rn.f32x2 + add.rn.f32x2 pairs anyway, so an "unfused" packed form cannot be expressed.
+// `math == B200OV_DW_EXACT` selects the pairwise kernel below, which is bit-identical to numpy.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+// S = stride (both directions).  A thread owns 4 channels x 2 adjacent output columns x a vertical strip of
+// `th` output rows and keeps the 3 x (S + 3) input window in registers: moving down one output row loads
+// S new input rows, i.e. (S + 3) * S / 2 128-bit loads per output instead of 9.  The row buffers rotate
+// by name (the loop is unrolled over one rotation period), and for S = 1 a fourth buffer receives the next
+// input row before the current output row is computed, so a load is always in flight behind the arithmetic.
+__device__ __align__(16) float g_dw_zeros[4];   // source of the np.pad zeros: padded taps load from here (no branches)
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float lo, float hi) {
+  if constexpr (ACT == B200OV_ACT_RELU) return v < 0.f ? 0.f : v;
+  else if constexpr (ACT == B200OV_ACT_CLAMP) return fminf(fmaxf(v, lo), hi);
+  else return v;
+}
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(128, 4) dwconv3x3_strip_kernel(DwStripP p, const float* __restrict__ x,
+                                                              const float* __restrict__ wp,
+                                                              const float* __restrict__ bias, float* __restrict__ y) {
+  constexpr int NC = S + 3;
+  constexpr int NB = S == 1 ? 4 : 3;     // row buffers
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += stride) {
+    uint32_t q, g, q2, oxt, img, strip;
+    p.d_cg.divmod(idx, q, g);
+    p.d_owt.divmod(q, q2, oxt);
+    p.d_strips.divmod(q2, img, strip);
+    const int c0 = (int)g * 4;
+    const int ox0 = (int)oxt * 2;
+    const int oy0 = (int)strip * p.th, oy1 = min(p.oh, oy0 + p.th);
+    const int ix0 = ox0 * S - p.pl;
+    const float* ximg = x + (size_t)img * p.h * p.w * p.x_ld + c0;
+    float* yp = y + ((size_t)(img * p.oh + oy0) * p.ow + ox0) * p.y_ld + c0;
+    ulonglong2 wt[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = __ldg(reinterpret_cast<const ulonglong2*>(wp + t * p.c + c0));
+    ulonglong2 bv = make_ulonglong2(0ull, 0ull);
+    if (bias != nullptr) bv = __ldg(reinterpret_cast<const ulonglong2*>(bias + c0));
+    const bool second = ox0 + 1 < p.ow;
+    int col_off[NC];                     // element offset of each window column inside an input row, -1 = padding
+#pragma unroll
+    for (int cidx = 0; cidx < NC; ++cidx) {
+      const bool ok = ix0 + cidx >= 0 && ix0 + cidx < p.w && (cidx < 3 || second);   // columns >= 3 only feed the 2nd output
+      col_off[cidx] = ok ? (ix0 + cidx) * p.x_ld : -1;
+    }
+    const ulonglong2* zeros = reinterpret_cast<const ulonglong2*>(g_dw_zeros);
+    ulonglong2 R[NB][NC];
+    auto load_row = [&](int iy, ulonglong2 (&dst)[NC]) {
+      const bool row_ok = iy >= 0 && iy < p.h;
+      const float* xr = ximg + (long long)(row_ok ? iy : 0) * p.w * p.x_ld;
+#pragma unroll
+      for (int cidx = 0; cidx < NC; ++cidx) {
+        const ulonglong2* src = (row_ok && col_off[cidx] >= 0) ? reinterpret_cast<const ulonglong2*>(xr + col_off[cidx]) : zeros;
+        dst[cidx] = __ldg(src);
+      }
+    };
+    // one output row (2 pixels x 4 channels) from the three buffered input rows
+    auto compute = [&](const ulonglong2 (&r0)[NC], const ulonglong2 (&r1)[NC], const ulonglong2 (&r2)[NC], float* yrow) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        f32x2 lo = bv.x, hi = bv.y;        // channels (0,1) and (2,3)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) { lo = fma2(r0[t * S + kx].x, wt[kx].x, lo); hi = fma2(r0[t * S + kx].y, wt[kx].y, hi); }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) { lo = fma2(r1[t * S + kx].x, wt[3 + kx].x, lo); hi = fma2(r1[t * S + kx].y, wt[3 + kx].y, hi); }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) { lo = fma2(r2[t * S + kx].x, wt[6 + kx].x, lo); hi = fma2(r2[t * S + kx].y, wt[6 + kx].y, hi); }
+        const float2 a = unpack2(lo), b = unpack2(hi);
+        const float4 o = make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
+                                     act_t<ACT>(b.y, p.lo, p.hi));
+        if (t == 0 || second) *reinterpret_cast<float4*>(yrow + t * p.y_ld) = o;
+      }
+    };
+    const size_t yrow_stride = (size_t)p.ow * p.y_ld;
+    const int iy_base = oy0 * S - p.pt;
+    if constexpr (S == 1) {
+      load_row(iy_base, R[0]);
+      load_row(iy_base + 1, R[1]);
+      load_row(iy_base + 2, R[2]);
+      for (int oy = oy0; oy < oy1; oy += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (oy + k < oy1) {
+            if (oy + k + 1 < oy1) load_row(iy_base + (oy + k + 1 - oy0) + 2, R[(k + 3) & 3]);   // next bottom row
+            compute(R[k & 3], R[(k + 1) & 3], R[(k + 2) & 3], yp);
+            yp += yrow_stride;
+          }
+        }
+      }
+    } else {
+      load_row(iy_base, R[0]);
+      for (int oy = oy0; oy < oy1; oy += 3) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (oy + k < oy1) {
+            const int iy = iy_base + (oy + k - oy0) * 2;
+            load_row(iy + 1, R[(2 * k + 1) % 3]);
+            load_row(iy + 2, R[(2 * k + 2) % 3]);
+            compute(R[(2 * k) % 3], R[(2 * k + 1) % 3], R[(2 * k + 2) % 3], yp);
+            yp += yrow_stride;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- generic window (runtime kh x kw), one output per thread --------------------------------------------
 // numpy `pairwise_sum` order for one run of KK float32 terms (KK <= 128):
 //   KK < 8  : sequential
 //   KK >= 8 : eight interleaved partial sums over the leading 8*floor(KK/8) terms, combined as
@@ -37,6 +174,12 @@ struct PairwiseAcc {
   int count = 0;
   int kk;
   __device__ explicit PairwiseAcc(int kk_) : kk(kk_) {}
+  __device__ void combine() {
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      tail[j] = __fadd_rn(__fadd_rn(__fadd_rn(r[0][j], r[1][j]), __fadd_rn(r[2][j], r[3][j])),
+                          __fadd_rn(__fadd_rn(r[4][j], r[5][j]), __fadd_rn(r[6][j], r[7][j])));
+  }
   __device__ void push(const float (&t)[V]) {
     const int full = (kk >= 8) ? (kk / 8) * 8 : 0;
     if (kk < 8) {
@@ -49,12 +192,7 @@ struct PairwiseAcc {
 #pragma unroll
       for (int j = 0; j < V; ++j) r[count & 7][j] = __fadd_rn(r[count & 7][j], t[j]);
     } else {
-      if (count == full) {
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-          tail[j] = __fadd_rn(__fadd_rn(__fadd_rn(r[0][j], r[1][j]), __fadd_rn(r[2][j], r[3][j])),
-                              __fadd_rn(__fadd_rn(r[4][j], r[5][j]), __fadd_rn(r[6][j], r[7][j])));
-      }
+      if (count == full) combine();
 #pragma unroll
       for (int j = 0; j < V; ++j) tail[j] = __fadd_rn(tail[j], t[j]);
     }
@@ -62,79 +200,44 @@ struct PairwiseAcc {
   }
   __device__ void finish(float (&out)[V]) {
     const int full = (kk >= 8) ? (kk / 8) * 8 : 0;
-    if (kk >= 8 && count == full) {
-#pragma unroll
-      for (int j = 0; j < V; ++j)
-        tail[j] = __fadd_rn(__fadd_rn(__fadd_rn(r[0][j], r[1][j]), __fadd_rn(r[2][j], r[3][j])),
-                            __fadd_rn(__fadd_rn(r[4][j], r[5][j]), __fadd_rn(r[6][j], r[7][j])));
-    }
+    if (kk >= 8 && count == full) combine();
 #pragma unroll
     for (int j = 0; j < V; ++j) out[j] = tail[j];
   }
 };
 
-// KH/KW > 0: compile-time window (fully unrolled, the 3x3 hot case); 0: runtime window.
-template <int V, int KH, int KW>
-__global__ void __launch_bounds__(256) dwconv_kernel(DwP p, const float* __restrict__ x, const float* __restrict__ wp,
-                                                     const float* __restrict__ bias, float* __restrict__ y) {
-  const int kh = KH > 0 ? KH : p.kh;
-  const int kw = KW > 0 ? KW : p.kw;
-  const int cg = p.c / V;
-  const long long total = (long long)p.n * p.oh * p.ow * cg;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % cg);
-    long long pix = idx / cg;
-    const int ox = (int)(pix % p.ow);
-    long long t = pix / p.ow;
-    const int oy = (int)(t % p.oh);
-    const int img = (int)(t / p.oh);
-    const int c0 = g * V;
-    const float* ximg = x + (long long)img * p.h * p.w * p.x_ld + c0;
-    const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
-    float res[V];
-    if constexpr (KH == 3 && KW == 3) {
-      float pr[9][V];
+template <int V>
+__global__ void __launch_bounds__(256) dwconv_generic_kernel(DwP p, const float* __restrict__ x, const float* __restrict__ wp,
+                                                             const float* __restrict__ bias, float* __restrict__ y) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += stride) {
+    uint32_t q, g;
+    p.d_cg.divmod(idx, q, g);
+    uint32_t q2, ox;
+    p.d_owt.divmod(q, q2, ox);                             // TW = 1 here: owt == ow
+    uint32_t img, oy;
+    p.d_oh.divmod(q2, img, oy);
+    const int c0 = (int)g * V;
+    const float* ximg = x + (size_t)img * p.h * p.w * p.x_ld + c0;
+    const int iy0 = (int)oy * p.sh - p.pt, ix0 = (int)ox * p.sw - p.pl;
+    PairwiseAcc<V> acc(p.kh * p.kw);
+    for (int ky = 0; ky < p.kh; ++ky)
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int iy = iy0 + ky, ix = ix0 + kx;
+        Vec<V> wv = Vec<V>::load(wp + (ky * p.kw + kx) * p.c + c0);
+        float term[V];
+        if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+          Vec<V> xv = Vec<V>::load(ximg + ((size_t)iy * p.w + ix) * p.x_ld);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+          for (int j = 0; j < V; ++j) term[j] = __fmul_rn(xv.v[j], wv.v[j]);
+        } else {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          Vec<V> wv = Vec<V>::load(wp + (ky * 3 + kx) * p.c + c0);
-          if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
-            Vec<V> xv = Vec<V>::load(ximg + ((long long)iy * p.w + ix) * p.x_ld);
-#pragma unroll
-            for (int j = 0; j < V; ++j) pr[ky * 3 + kx][j] = __fmul_rn(xv.v[j], wv.v[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) pr[ky * 3 + kx][j] = __fmul_rn(0.f, wv.v[j]);
-          }
+          for (int j = 0; j < V; ++j) term[j] = __fmul_rn(0.f, wv.v[j]);
         }
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float s01 = __fadd_rn(pr[0][j], pr[1][j]), s23 = __fadd_rn(pr[2][j], pr[3][j]);
-        float s45 = __fadd_rn(pr[4][j], pr[5][j]), s67 = __fadd_rn(pr[6][j], pr[7][j]);
-        res[j] = __fadd_rn(__fadd_rn(__fadd_rn(s01, s23), __fadd_rn(s45, s67)), pr[8][j]);
+        acc.push(term);
       }
-    } else {
-      PairwiseAcc<V> acc(kh * kw);
-      for (int ky = 0; ky < kh; ++ky)
-        for (int kx = 0; kx < kw; ++kx) {
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          Vec<V> wv = Vec<V>::load(wp + (ky * kw + kx) * p.c + c0);
-          float term[V];
-          if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
-            Vec<V> xv = Vec<V>::load(ximg + ((long long)iy * p.w + ix) * p.x_ld);
-#pragma unroll
-            for (int j = 0; j < V; ++j) term[j] = __fmul_rn(xv.v[j], wv.v[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) term[j] = __fmul_rn(0.f, wv.v[j]);
-          }
-          acc.push(term);
-        }
-      acc.finish(res);
-    }
+    float res[V];
+    acc.finish(res);
     Vec<V> out;
     if (bias != nullptr) {
       Vec<V> bv = Vec<V>::load(bias + c0);
@@ -144,7 +247,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwP p, const float* __restr
 #pragma unroll
       for (int j = 0; j < V; ++j) out.v[j] = apply_act(res[j], p.act, p.lo, p.hi);
     }
-    out.store(y + pix * p.y_ld + c0);
+    out.store(y + ((size_t)(img * p.oh + oy) * p.ow + ox) * p.y_ld + c0);
   }
 }
 
@@ -178,19 +281,52 @@ int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_
   B200OV_REQUIRE(d->x_ld >= d->c && d->y_ld >= d->c, "dwconv2d: channel pitch smaller than channel count");
   B200OV_REQUIRE(d->kh * d->kw <= 128, "dwconv2d: window larger than 128 taps is not supported");
   B200OV_REQUIRE(d->act >= B200OV_ACT_NONE && d->act <= B200OV_ACT_SIGMOID, "dwconv2d: bad activation");
-  DwP p{d->n, d->h, d->w, d->c, d->kh, d->kw, d->sh, d->sw, d->pt, d->pl, d->oh, d->ow, d->x_ld, d->y_ld, d->act,
-        d->act_lo, d->act_hi};
+  B200OV_REQUIRE(d->math == B200OV_DW_AUTO || d->math == B200OV_DW_EXACT, "dwconv2d: bad math mode");
   if (d->n == 0) return B200OV_OK;
   cudaStream_t s = as_stream(stream);
   const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned16(x) && aligned16(y) &&
                    aligned16(w_packed) && (bias == nullptr || aligned16(bias));
-  const bool k3 = d->kh == 3 && d->kw == 3;
-  long long total = (long long)d->n * d->oh * d->ow * (vec ? d->c / 4 : d->c);
-  int grid = bw_grid(total, 256);
-  if (vec && k3) dwconv_kernel<4, 3, 3><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
-  else if (vec) dwconv_kernel<4, 0, 0><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
-  else if (k3) dwconv_kernel<1, 3, 3><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
-  else dwconv_kernel<1, 0, 0><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
+  const int V = vec ? 4 : 1;
+  const int cg = d->c / V;
+  if (vec && d->math != B200OV_DW_EXACT && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) {
+    DwStripP q;
+    q.h = d->h; q.w = d->w; q.c = d->c; q.pt = d->pt; q.pl = d->pl; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld;
+    q.y_ld = d->y_ld; q.act = d->act; q.lo = d->act_lo; q.hi = d->act_hi;
+    q.th = d->oh < 8 ? d->oh : 8;
+    const int strips = ceil_div(d->oh, q.th), owt = ceil_div(d->ow, 2);
+    const long long items = (long long)d->n * strips * owt * cg;
+    if (items < 0x7fffffffLL) {
+      q.total = (uint32_t)items;
+      q.d_cg = FastDiv(cg); q.d_owt = FastDiv(owt); q.d_strips = FastDiv(strips);
+      const int g = bw_grid(items, 128, 16);
+#define B200OV_DW_LAUNCH(S_, A_) dwconv3x3_strip_kernel<S_, A_><<<g, 128, 0, s>>>(q, x, w_packed, bias, y)
+      if (d->act <= B200OV_ACT_CLAMP) {
+        if (d->sh == 1) {
+          if (d->act == B200OV_ACT_NONE) B200OV_DW_LAUNCH(1, B200OV_ACT_NONE);
+          else if (d->act == B200OV_ACT_RELU) B200OV_DW_LAUNCH(1, B200OV_ACT_RELU);
+          else B200OV_DW_LAUNCH(1, B200OV_ACT_CLAMP);
+        } else {
+          if (d->act == B200OV_ACT_NONE) B200OV_DW_LAUNCH(2, B200OV_ACT_NONE);
+          else if (d->act == B200OV_ACT_RELU) B200OV_DW_LAUNCH(2, B200OV_ACT_RELU);
+          else B200OV_DW_LAUNCH(2, B200OV_ACT_CLAMP);
+        }
+#undef B200OV_DW_LAUNCH
+        B200OV_LAUNCH_CHECK("dwconv3x3_strip_kernel");
+        return B200OV_OK;
+      }
+    }
+  }
+  DwP p;
+  p.n = d->n; p.h = d->h; p.w = d->w; p.c = d->c; p.kh = d->kh; p.kw = d->kw; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt;
+  p.pl = d->pl; p.oh = d->oh; p.ow = d->ow; p.x_ld = d->x_ld; p.y_ld = d->y_ld; p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
+  p.owt = d->ow;
+  long long total = (long long)d->n * d->oh * p.owt * cg;
+  B200OV_REQUIRE(total < 0x7fffffffLL, "dwconv2d: problem too large for 32-bit indexing");
+  p.total = (uint32_t)total;
+  p.d_cg = FastDiv(cg); p.d_owt = FastDiv(p.owt); p.d_oh = FastDiv(d->oh);
+  const int grid = bw_grid(total, 256);
+  if (vec) dwconv_generic_kernel<4><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
+  else dwconv_generic_kernel<1><<<grid, 256, 0, s>>>(p, x, w_packed, bias, y);
   B200OV_LAUNCH_CHECK("dwconv_kernel");
   return B200OV_OK;
 }

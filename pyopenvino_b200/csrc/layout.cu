@@ -44,6 +44,47 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// NCHW -> NHWC for few channels (the network input: C = 1 or 3).  The tiled transpose above wastes most
+// of its 32-row tile here; instead a thread owns one pixel, reads its C planes (coalesced across the warp)
+// and writes the pixel's channel run.  PAD4: y_ld == 4 >= C, one 128-bit store per pixel with the unused
+// lanes zeroed (the tcgen05 stem convolution gathers 16-byte channel runs and needs finite padding).
+template <int MAXC, bool PAD4>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                  long long pixels, int c, int hw, int y_ld, int has_scale,
+                                                                  const float* __restrict__ scale_vec, float scale_s,
+                                                                  int has_shift, const float* __restrict__ shift_vec,
+                                                                  float shift_s) {
+  float sc[MAXC], sf[MAXC];
+#pragma unroll
+  for (int ch = 0; ch < MAXC; ++ch) {
+    sc[ch] = (has_scale && ch < c) ? (scale_vec ? __ldg(scale_vec + ch) : scale_s) : 1.f;
+    sf[ch] = (has_shift && ch < c) ? (shift_vec ? __ldg(shift_vec + ch) : shift_s) : 0.f;
+  }
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < pixels;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long img = pix / hw;
+    const int r = (int)(pix - img * hw);
+    const float* xp = x + img * c * hw + r;
+    float v[MAXC];
+#pragma unroll
+    for (int ch = 0; ch < MAXC; ++ch) {
+      v[ch] = 0.f;
+      if (ch < c) {
+        v[ch] = __ldg(xp + (long long)ch * hw);
+        if (has_scale) v[ch] = __fmul_rn(v[ch], sc[ch]);
+        if (has_shift) v[ch] = __fadd_rn(v[ch], sf[ch]);
+      }
+    }
+    if constexpr (PAD4) {
+      *reinterpret_cast<float4*>(y + pix * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < MAXC; ++ch)
+        if (ch < c) y[pix * y_ld + ch] = v[ch];
+    }
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                      long long rows, int cols, int src_ld, int dst_ld) {
@@ -92,6 +133,18 @@ int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, i
                                const float* scale_vec, float scale_s, int has_shift, const float* shift_vec,
                                float shift_s, void* stream) {
   B200OV_REQUIRE(x && y && n >= 0 && c > 0 && hw > 0 && y_ld >= c, "nchw_to_nhwc_affine: bad argument");
+  if (c <= 4 && n > 0) {
+    const long long pixels = (long long)n * hw;
+    cudaStream_t s = as_stream(stream);
+    if (y_ld == 4 && aligned16(y))
+      nchw_to_nhwc_smallc_kernel<4, true><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                              scale_s, has_shift, shift_vec, shift_s);
+    else
+      nchw_to_nhwc_smallc_kernel<4, false><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                               scale_s, has_shift, shift_vec, shift_s);
+    B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
+    return B200OV_OK;
+  }
   return launch_transpose(true, x, y, n, c, hw, hw, y_ld, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s,
                           as_stream(stream));
 }

@@ -6,8 +6,15 @@
 //          (min(h, ...), :69).
 // AvgPool  (AvgPool.py:41-59): no padding is applied and the window is clipped at h-1 / w-1
 //          (:56), so the 7x7 GoogLeNet pool averages rows/cols 0..5 only.
-// Bandwidth-bound: one thread owns V consecutive channels of one output pixel (128-bit accesses).
+// Bandwidth-bound.  Two kernels:
+//   pool_max_strip_kernel : the MaxPool hot case (compile-time window / stride).  A thread owns 4 consecutive
+//       channels (128-bit accesses) of a vertical strip of TH output pixels and keeps the per-row maxima of
+//       the rows two neighbouring windows share in registers, so a 3x3 stride-1 pool issues 3 loads per
+//       output instead of 9 (the LSU / L1 wavefront rate, not HBM, is what limits the naive form).
+//       32-bit index arithmetic with multiply-high division (fastdiv.cuh).
+//   pool_kernel           : every other window (and AvgPool), one thread per output, runtime loops.
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b200ov {
 
@@ -28,6 +35,91 @@ template <int V>
 __device__ __forceinline__ void storev(float* p, const float (&v)[V]) {
   if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   else *p = v[0];
+}
+
+struct PoolStripP {
+  int h, w, sw, pt, pl, hp, wpad, oh, ow, x_ld, y_ld, th;
+  uint32_t total;                // work items = n * strips * ow * cg
+  FastDiv d_cg, d_ow, d_strips;
+};
+
+// MaxPool, window KH x KW, row stride SH (column stride runtime), V = 4 channels per thread.
+template <int KH, int KW, int SH>
+__global__ void __launch_bounds__(256) pool_max_strip_kernel(PoolStripP p, const float* __restrict__ x,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, float* __restrict__ y) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += stride) {
+    uint32_t q, g, q2, ox, img, strip;
+    p.d_cg.divmod(idx, q, g);
+    p.d_ow.divmod(q, q2, ox);
+    p.d_strips.divmod(q2, img, strip);
+    const int c0 = (int)g * 4;
+    const int oy0 = (int)strip * p.th;
+    const int oy1 = min(p.oh, oy0 + p.th);
+    const float* ximg = x + (size_t)img * p.h * p.w * p.x_ld + c0;
+    float* yp = y + ((size_t)(img * p.oh + oy0) * p.ow + ox) * p.y_ld + c0;
+    const int px0 = (int)ox * p.sw;
+    const int ix0 = px0 - p.pl;
+    // column validity of the window (fixed for the strip): inside the padded tensor / inside the real tensor
+    bool col_in_pad[KW], col_in_x[KW];
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      col_in_pad[kx] = px0 + kx < p.wpad;
+      col_in_x[kx] = ix0 + kx >= 0 && ix0 + kx < p.w;
+    }
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale != nullptr) sc = __ldg(reinterpret_cast<const float4*>(scale + c0));
+    if (shift != nullptr) sf = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    // maximum over the window columns of padded row py; -inf when the row lies outside the padded tensor
+    auto row_max = [&](int py) -> float4 {
+      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (py >= p.hp) return m;
+      const int iy = py - p.pt;
+      const bool row_in = iy >= 0 && iy < p.h;
+      const float* xr = ximg + ((long long)(row_in ? iy : 0) * p.w + ix0) * p.x_ld;
+      float4 v[KW];
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        v[kx] = make_float4(0.f, 0.f, 0.f, 0.f);                       // the zero padding participates
+        if (row_in && col_in_x[kx]) v[kx] = __ldg(reinterpret_cast<const float4*>(xr + kx * p.x_ld));
+      }
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx)
+        if (col_in_pad[kx]) {
+          m.x = fmaxf(m.x, v[kx].x); m.y = fmaxf(m.y, v[kx].y); m.z = fmaxf(m.z, v[kx].z); m.w = fmaxf(m.w, v[kx].w);
+        }
+      return m;
+    };
+    // Two output rows per iteration: their 2*SH new input rows are all requested before the first max is
+    // taken, so each thread keeps 2*SH*KW 128-bit loads in flight (the kernel is latency-, not LSU-bound).
+    constexpr int KEEP = KH > SH ? KH - SH : 0;      // rows shared by vertically adjacent windows
+    constexpr int NR = KH + SH;                      // padded rows under two vertically adjacent windows
+    float4 rm[NR];
+#pragma unroll
+    for (int r = 0; r < KEEP; ++r) rm[r] = row_max(oy0 * SH + r);
+    for (int oy = oy0; oy < oy1; oy += 2) {
+      const bool two = oy + 1 < oy1;
+#pragma unroll
+      for (int r = KEEP; r < NR; ++r) rm[r] = row_max((two || r < KH) ? oy * SH + r : p.hp);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !two) break;
+        float4 o = rm[t * SH];
+#pragma unroll
+        for (int r = 1; r < KH; ++r) {
+          const float4 m = rm[t * SH + r];
+          o.x = fmaxf(o.x, m.x); o.y = fmaxf(o.y, m.y); o.z = fmaxf(o.z, m.z); o.w = fmaxf(o.w, m.w);
+        }
+        if (scale != nullptr) { o.x = __fmul_rn(o.x, sc.x); o.y = __fmul_rn(o.y, sc.y); o.z = __fmul_rn(o.z, sc.z); o.w = __fmul_rn(o.w, sc.w); }
+        if (shift != nullptr) { o.x = __fadd_rn(o.x, sf.x); o.y = __fadd_rn(o.y, sf.y); o.z = __fadd_rn(o.z, sf.z); o.w = __fadd_rn(o.w, sf.w); }
+        *reinterpret_cast<float4*>(yp) = o;
+        yp += (size_t)p.ow * p.y_ld;
+      }
+#pragma unroll
+      for (int r = 0; r < KEEP; ++r) rm[r] = rm[r + 2 * SH];
+    }
+  }
 }
 
 template <int V>
@@ -121,6 +213,26 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   if (d->n == 0) return B200OV_OK;
   const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned16(x) && aligned16(y) &&
                    (scale == nullptr || aligned16(scale)) && (shift == nullptr || aligned16(shift));
+  if (vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && (d->sh == 1 || d->sh == 2)) {
+    PoolStripP q;
+    q.h = d->h; q.w = d->w; q.sw = d->sw; q.pt = d->pt; q.pl = d->pl; q.hp = d->h + d->pt + d->pb;
+    q.wpad = d->w + d->pl + d->pr; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld; q.y_ld = d->y_ld;
+    q.th = d->oh < 8 ? d->oh : 8;
+    const int strips = ceil_div(d->oh, q.th), cg = d->c / 4;
+    const long long items = (long long)d->n * strips * d->ow * cg;
+    if (items < 0x7fffffffLL) {
+      q.total = (uint32_t)items;
+      q.d_cg = FastDiv(cg); q.d_ow = FastDiv(d->ow); q.d_strips = FastDiv(strips);
+      const int g = bw_grid(items, 256);
+      cudaStream_t s = as_stream(stream);
+      if (d->kh == 3 && d->sh == 1) pool_max_strip_kernel<3, 3, 1><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else if (d->kh == 3) pool_max_strip_kernel<3, 3, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else if (d->sh == 1) pool_max_strip_kernel<2, 2, 1><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else pool_max_strip_kernel<2, 2, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      B200OV_LAUNCH_CHECK("pool_max_strip_kernel");
+      return B200OV_OK;
+    }
+  }
   long long total = (long long)d->n * d->oh * d->ow * (vec ? d->c / 4 : d->c);
   int grid = bw_grid(total, 256);
   if (vec) pool_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);

@@ -233,7 +233,7 @@ def pack_dw(w):
     return w.cache['dw']
 
 
-def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None):
+def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, exact=False):
     x = as_nhwc(x)
     t, g, kh, kw = pack_dw(w)
     n, c, h, wd = x.shape
@@ -243,7 +243,8 @@ def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None):
     out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
     code, lo, hi = _act(act)
     d = _cabi.DwConvDesc(n=n, h=h, w=wd, c=c, kh=kh, kw=kw, sh=strides[0], sw=strides[1], pt=pads_begin[0],
-                         pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, act=code, act_lo=lo, act_hi=hi)
+                         pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, act=code, act_lo=lo, act_hi=hi,
+                         math=_cabi.DW_EXACT if exact else _cabi.DW_AUTO)
     b = _vec_ptr(bias, c)
     _cabi.call('b200ov_dwconv2d', C.byref(d), _p(x), C.c_void_p(t.data_ptr()), _p(b), _p(out), _s())
     return out

@@ -40,9 +40,14 @@ def _node(i, m):
 def test_plugin_vs_reference_vectors(i, plugins):
     m = META[i]
     node, ins, op = _node(i, m)
-    res = plugins[m['type']].compute(node, dict(ins), kernel_type='numpy')
-    got = np.asarray(res[op])
     want = OPS['c{}_out_numpy'.format(i)]
+    if m['type'] == 'GroupConvolution':
+        # default kernel = packed-FMA chain (tolerance class); 'exact' = pairwise kernel, bit-identical (checked below)
+        fast = np.asarray(plugins[m['type']].compute(node, dict(ins), kernel_type='numpy')[op])
+        ok, msg = close(fast, want)
+        assert ok, (m['tag'], msg)
+    res = plugins[m['type']].compute(node, dict(ins), kernel_type='exact' if m['type'] == 'GroupConvolution' else 'numpy')
+    got = np.asarray(res[op])
     assert got.shape == want.shape, (got.shape, want.shape)
     assert got.dtype == want.dtype
     if m['type'] in BIT_EXACT:
@@ -126,7 +131,8 @@ def test_conv_layer_shapes_vs_oracle(shape, plugins):
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 150, 1, (1, 1), (1, 1)), (2, 64, 150, 2, (0, 0), (1, 1)), (3, 128, 75, 2, (1, 1), (1, 1)),
-                                   (2, 512, 19, 1, (1, 1), (1, 1)), (2, 1024, 10, 1, (1, 1), (1, 1)), (1, 6, 7, 1, (1, 1), (1, 1))])
+                                   (2, 512, 19, 1, (1, 1), (1, 1)), (2, 1024, 10, 1, (1, 1), (1, 1)), (1, 6, 7, 1, (1, 1), (1, 1)),
+                                   (2, 8, 9, 2, (0, 0), (1, 1)), (1, 16, 21, 2, (1, 1), (1, 1)), (2, 4, 5, 1, (1, 1), (1, 1))])
 def test_depthwise_bit_exact_vs_oracle(shape, plugins):
     from oracle import ref_ops
     n, c, hw, s, pb, pe = shape
@@ -138,13 +144,19 @@ def test_depthwise_bit_exact_vs_oracle(shape, plugins):
     node = {'name': 'dw', 'type': 'GroupConvolution', 'data': data,
             'input': {0: {'precision': 'FP32', 'dims': x.shape}, 1: {'precision': 'FP32', 'dims': w.shape}},
             'output': {2: {'precision': 'FP32', 'dims': ()}}}
-    got = plugins['GroupConvolution'].compute(node, {0: x, 1: w}, kernel_type='numpy')[2]
     want = ref_ops.groupconv_numpy(x, w, (s, s), pb, pe, 'explicit')
-    assert np.array_equal(got, want), np.abs(got - want).max()
+    got = plugins['GroupConvolution'].compute(node, {0: x, 1: w}, kernel_type='exact')[2]
+    assert np.array_equal(got, want), np.abs(got - want).max()        # pairwise kernel: bit-identical to np.sum
+    fast = plugins['GroupConvolution'].compute(node, {0: x, 1: w}, kernel_type='numpy')[2]
+    ok, msg = close(fast, want)                                         # packed-FMA 3x3 kernel: FP32 tolerance class
+    assert ok, (shape, msg)
+    assert np.abs(fast - want).max() <= 4e-6, np.abs(fast - want).max()
 
 
 @pytest.mark.parametrize('shape', [(2, 64, 112, 3, 2, (0, 0), 'ceil'), (2, 192, 28, 3, 1, (1, 1), 'ceil'), (3, 832, 7, 3, 1, (1, 1), 'ceil'),
-                                   (4, 32, 26, 2, 2, (0, 0), 'floor'), (2, 10, 11, 2, 2, (0, 0), 'floor')])
+                                   (4, 32, 26, 2, 2, (0, 0), 'floor'), (2, 10, 11, 2, 2, (0, 0), 'floor'),
+                                   (2, 8, 19, 3, 2, (1, 1), 'ceil'), (1, 12, 23, 3, 2, (0, 0), 'floor'), (2, 4, 9, 2, 1, (0, 0), 'floor'),
+                                   (1, 16, 17, 3, 1, (0, 0), 'floor')])
 def test_maxpool_bit_exact_vs_oracle(shape, plugins):
     from oracle import ref_ops
     n, c, hw, k, s, p, rounding = shape

@@ -72,7 +72,7 @@ def main():
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}
     rng = np.random.default_rng(0)
-    flush = torch.empty(64 << 20, dtype=torch.float32, device='cuda')
+    flush = torch.empty(128 << 20, dtype=torch.float32, device='cuda')   # 512 MB: flushes L2 and gives the host a head start
     stream = torch.cuda.Stream()
     B = args.batch
     rows = []
