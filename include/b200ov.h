@@ -49,10 +49,12 @@ enum {
 
 /* arithmetic used by the dense contractions */
 enum {
-  B200OV_MATH_AUTO = 0,     /* pick per shape: tcgen05 3xTF32 when eligible, else FP32 FFMA */
+  B200OV_MATH_AUTO = 0,     /* pick per shape: F16X2 when eligible, else 3xTF32, else FP32 FFMA */
   B200OV_MATH_FP32 = 1,     /* CUDA-core FP32 FFMA implicit GEMM                                */
   B200OV_MATH_TF32X3 = 2,   /* tcgen05 kind::tf32, hi/lo split, 3 MMAs, FP32 accumulate in TMEM */
-  B200OV_MATH_TF32 = 3      /* tcgen05 kind::tf32 single pass (1e-3 tolerance class)            */
+  B200OV_MATH_TF32 = 3,     /* tcgen05 kind::tf32 single pass (1e-3 tolerance class)            */
+  B200OV_MATH_F16X2 = 4     /* tcgen05 kind::f16, FP16 hi/lo split, 3 MMAs, A operand in TMEM;  *
+                             * FP32-accurate for |values| < 65504, overflow raises the status word */
 };
 
 /* ---- library / device -------------------------------------------------------------------- */
@@ -113,6 +115,13 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
 int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw,
                   const float* bias, int act, float act_lo, float act_hi, int math,
                   float* y, int ldy, void* stream);
+
+/* Device address of the library's sticky status word (uint32).  Bit 0 is set by a B200OV_MATH_F16X2
+ * contraction whose output held a non-finite value (an operand beyond the FP16 range, or inf/NaN data).
+ * The executor clears it before an inference (cudaMemsetAsync), reads it back with the results and, if set,
+ * repeats the inference with B200OV_MATH_TF32X3.  The reference has no such condition: its numpy kernels
+ * compute in FP32 throughout (Convolution.py:83-84). */
+int b200ov_status_word(void** device_ptr);
 
 /* ---- depthwise GroupConvolution ------------------------------------------------------------ */
 typedef struct {

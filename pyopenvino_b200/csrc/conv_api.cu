@@ -6,6 +6,12 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
 // tcgen05 path (gemm_tcgen05.cu): returns B200OV_ERR_UNSUPPORTED when the shape is not eligible
 int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
                    cudaStream_t s, bool probe_only);
+// persistent tcgen05 FP16-split path (conv_f16x2.cu)
+bool f16x2_eligible(const b200ov_conv_desc* d, const float* x);
+int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s);
+unsigned int* f16x2_status_word();
+bool has_tf32_section(int cin);
+void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* kpad);
 }  // namespace b200ov
 
 using namespace b200ov;
@@ -24,9 +30,19 @@ static int validate(const b200ov_conv_desc* d, const float* x, const float* wp, 
   return B200OV_OK;
 }
 
-// the tf32 section follows the FP32 section inside the packed weight buffer
+// packed weight buffer: [FP32 section | tf32 hi/lo planes (when eligible) | f16 hi/lo planes]
 static const float* tf32_section(const b200ov_conv_desc* d, const float* w_packed) {
   return w_packed + (long long)round_up(d->kh * d->kw * d->cin, 16) * d->ldw;
+}
+static const float* f16_section(const b200ov_conv_desc* d, const float* w_packed) {
+  const float* p = tf32_section(d, w_packed);
+  if (has_tf32_section(d->cin)) {
+    int coutp;
+    long long kpad;
+    tf32_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad);
+    p += 2LL * coutp * kpad;
+  }
+  return p;
 }
 
 extern "C" {
@@ -42,7 +58,10 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
     case B200OV_MATH_TF32X3:
     case B200OV_MATH_TF32:
       return conv2d_tcgen05(d, x, tf32_section(d, w_packed), bias, y, s, false);
+    case B200OV_MATH_F16X2:
+      return conv2d_f16x2(d, x, f16_section(d, w_packed), bias, y, s);
     case B200OV_MATH_AUTO: {
+      if (f16x2_eligible(d, x)) return conv2d_f16x2(d, x, f16_section(d, w_packed), bias, y, s);
       if (conv2d_tcgen05(d, x, nullptr, bias, y, s, true) == B200OV_OK) {
         b200ov_conv_desc dd = *d;
         dd.math = B200OV_MATH_TF32X3;
@@ -66,6 +85,17 @@ int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_p
   d.act = act; d.act_lo = act_lo; d.act_hi = act_hi; d.math = math;
   if (m == 0) return B200OV_OK;
   return b200ov_conv2d(&d, a, b_packed, bias, y, stream);
+}
+
+/* Sticky device status word (bit 0: a non-finite value left an f16x2 contraction, i.e. an operand exceeded the
+ * FP16 range or the data held inf/NaN).  The caller resets it (cudaMemsetAsync) before an inference and reads
+ * it back with the results; if set, re-run with B200OV_MATH_TF32X3. */
+int b200ov_status_word(void** device_ptr) {
+  B200OV_REQUIRE(device_ptr, "status_word: null argument");
+  unsigned int* p = f16x2_status_word();
+  if (p == nullptr) return set_error(B200OV_ERR_CUDA, "status_word: cudaGetSymbolAddress failed");
+  *device_ptr = p;
+  return B200OV_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,606 @@
+// Persistent tcgen05 / TMEM / TMA implicit-GEMM convolution + MatMul for sm_100a, FP32-accurate through a
+// two-term FP16 split ("f16x2"):  a = a_hi + 2^-11 a_lo',  w = w_hi + 2^-11 w_lo'  (each part an FP16 number,
+// 11 + 11 significant bits), and
+//
+//     sum a*w  =  sum a_hi*w_hi  +  2^-11 * sum (a_lo'*w_hi + a_hi*w_lo')   + O(2^-22 |a||w|)
+//
+// i.e. three kind::f16 MMAs per product: the same accuracy class as 3xTF32 at twice the tensor-pipe rate and
+// half the operand bytes.  FP16 has a 5-bit exponent, so inputs beyond +-65504 overflow: the epilogue raises a
+// sticky status flag when it sees a non-finite output and the engine re-runs the inference on the 3xTF32 path
+// (gemm_tcgen05.cu).  Values below the FP16 normal range are still covered: the scaled residual keeps the
+// absolute error below 2^-36.
+//
+// GEMM view (reference: Convolution.py:57-87):  D[M pixels][N cout] = A[M][K] * W[N][K]^T.  K is cut into
+// units of 8 channels of one filter tap (cin padded to 8), 4 units = one 32-wide "slot".
+//
+// Warp roles (320 threads, one persistent CTA per SM, static round-robin tile schedule):
+//   warp 0      B loader : TMA loads of the pre-split FP16 weight tiles (hi / lo planes, 64 K-elements per
+//                          stage, 128B swizzle) into a shared-memory ring.
+//   warp 1      MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
+//                          shared memory; tcgen05.commit releases A slots / B stages / accumulators.
+//   warps 2-5   A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
+//                          4 threads cover one pixel's 32-channel run, software-pipelined 3 slots deep, running
+//                          ahead across tile boundaries), FP32 -> FP16 hi/lo split with packed FP32 math, and
+//                          tcgen05.st into a 4-slot TMEM ring.  The A operand never touches shared memory: the
+//                          MMA reads of B alone already use ~60% of the 128 B/clk shared-memory port.
+//   warps 6-9   epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
+//                          see below), add the cross terms, bias, activation, stage the tile in shared memory
+//                          and write it with TMA stores (coalesced, asynchronous), overlapping the next tile.
+//
+// Accuracy engineering (as in gemm_tcgen05.cu): the tensor core truncates when it adds into the FP32
+// accumulator.  The hi*hi accumulator therefore ping-pongs between two TMEM buffers and is added into
+// registers with round-to-nearest every CHUNK slots; the cross terms (2^-11 smaller) keep their own
+// accumulator for the whole tile.  Tests hold the result to |d| <= 1e-5 + 1e-4|ref| against the oracle.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "fastdiv.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200ov {
+
+namespace f16 {
+
+using namespace ptx;
+
+constexpr int BLOCK_M = 128;
+constexpr int SLOT_K = 32;             // K elements per A slot (4 units of 8 channels)
+constexpr int A_SLOTS = 4;             // TMEM ring depth
+constexpr int A_COL0 = 384;            // TMEM columns [384, 512): A ring, 32 columns per slot (16 hi + 16 lo)
+constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
+constexpr int CHUNK = 2;               // slots per promotion chunk (64 K elements)
+constexpr int NUM_THREADS = 320;
+constexpr int NUM_PRODUCERS = 128;
+constexpr int NUM_EPILOGUE = 128;
+constexpr int EPI_BAR_ID = 1;
+constexpr float LO_SCALE = 2048.f;     // 2^11
+constexpr float LO_UNSCALE = 1.f / 2048.f;
+
+struct Params {
+  int h, w, cin, cout, sh, sw, pt, pl, x_ld, y_ld;
+  int M, num_slots, units, tiles_n, num_tiles;
+  int act;
+  float lo, hi;
+  int tma_store;                       // 1: output written by TMA (y 16-byte aligned, y_ld % 4 == 0)
+  int wide_loads;                      // 1: 256-bit gathers (x 32-byte aligned, x_ld % 8 == 0)
+  FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots;
+};
+
+__device__ __align__(32) float g_zero_run[8];      // source of the np.pad zeros
+
+template <int BLOCK_N, int SB>
+struct Smem {
+  static constexpr int B_PLANE_BYTES = BLOCK_N * 128;                  // one stage of one plane: BLOCK_N rows x 64 halfs
+  static constexpr int B_HI = 0;
+  static constexpr int B_LO = B_HI + SB * B_PLANE_BYTES;
+  static constexpr int STAGING = B_LO + SB * B_PLANE_BYTES;            // 4 warps x (BLOCK_N / 32) blocks x 4 KB
+  static constexpr int STAGING_BYTES = 4 * (BLOCK_N / 32) * 4096;
+  static constexpr int BIAS = STAGING + STAGING_BYTES;                 // BLOCK_N floats
+  static constexpr int BARS = BIAS + BLOCK_N * 4;
+  // b_full[SB], b_empty[SB], a_full[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full, cross_empty
+  static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 6;
+  static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16 + 1024;                   // + slack for the 1024-byte alignment of the base
+};
+
+__device__ __forceinline__ constexpr uint32_t instr_desc(int block_n) {
+  return (1u << 4)                                   // D format: F32;  A, B format F16 (0), both K-major, no negate
+         | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f32x2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// (c0, c1) -> packed FP16 hi pair and scaled-residual lo pair:  c = hi + 2^-11 lo  up to 2^-22 |c|.
+// (c - hi) is exact in FP32 and so is its 2^11 scaling, hence fma(c, 2^11, -(2^11 hi)) is exact too.
+__device__ __forceinline__ void split_pair(float c0, float c1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(c0, c1);
+  const float2 hf = __half22float2(h);
+  const f32x2 neg = mul2(pack_f32x2(hf.x, hf.y), pack_f32x2(-LO_SCALE, -LO_SCALE));
+  const float2 r = unpack_f32x2(fma2(pack_f32x2(c0, c1), pack_f32x2(LO_SCALE, LO_SCALE), neg));
+  const __half2 l = __floats2half2_rn(r.x, r.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct Run8 {
+  float v[8];
+};
+__device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
+  Run8 r;
+  if (wide) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  }
+  return r;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float lo, float hi) {
+  if constexpr (ACT == B200OV_ACT_RELU) return v < 0.f ? 0.f : v;
+  else if constexpr (ACT == B200OV_ACT_CLAMP) return fminf(fmaxf(v, lo), hi);
+  else if constexpr (ACT == B200OV_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  else return v;
+}
+
+template <int BLOCK_N, int SB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+                  unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
+                  const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y) {
+  using L = Smem<BLOCK_N, SB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  auto bar_b_full = [&](int s) { return base + L::BARS + 8 * s; };
+  auto bar_b_empty = [&](int s) { return base + L::BARS + 8 * (SB + s); };
+  auto bar_a_full = [&](int s) { return base + L::BARS + 8 * (2 * SB + s); };
+  auto bar_a_empty = [&](int s) { return base + L::BARS + 8 * (2 * SB + A_SLOTS + s); };
+  auto bar_main_full = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + i); };
+  auto bar_main_empty = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 2 + i); };
+  const uint32_t bar_cross_full = base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 4);
+  const uint32_t bar_cross_empty = base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 5);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_PTR);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bar_b_full(s), 1);
+      mbar_init(bar_b_empty(s), 1);
+    }
+    for (int s = 0; s < A_SLOTS; ++s) {
+      mbar_init(bar_a_full(s), NUM_PRODUCERS);
+      mbar_init(bar_a_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_main_full(i), 1);
+      mbar_init(bar_main_empty(i), NUM_EPILOGUE);
+    }
+    mbar_init(bar_cross_full, 1);
+    mbar_init(bar_cross_empty, NUM_EPILOGUE);
+    fence_mbar_init();
+    prefetch_tensormap(&map_hi);
+    prefetch_tensormap(&map_lo);
+    prefetch_tensormap(&map_y);
+  }
+  if (warp == 1) tmem_alloc(base + L::TMEM_PTR, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int num_stages = (p.num_slots + 1) >> 1;      // B stages per tile
+
+  if (warp == 0) {
+    // ================= B loader ======================================================================
+    if (lane == 0) {
+      uint32_t bcount = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
+        const int n0 = (int)(tile - p.d_tiles_n.div(tile) * p.d_tiles_n.d) * BLOCK_N;
+        for (int ks = 0; ks < num_stages; ++ks, ++bcount) {
+          const int s = bcount % SB;
+          mbar_wait(bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_b_full(s), 2 * L::B_PLANE_BYTES);
+          tma_load_2d(base + L::B_HI + s * L::B_PLANE_BYTES, &map_hi, ks * STAGE_K, n0, bar_b_full(s));
+          tma_load_2d(base + L::B_LO + s * L::B_PLANE_BYTES, &map_lo, ks * STAGE_K, n0, bar_b_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer ====================================================================
+    constexpr uint32_t idesc = instr_desc(BLOCK_N);
+    const uint32_t tmem_cross = tmem_base + 2 * BLOCK_N;
+    uint32_t acount = 0, bcount = 0, chunkcount = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      for (int slot = 0; slot < p.num_slots; ++slot) {
+        const bool last = slot == p.num_slots - 1;
+        const int buf = chunkcount & 1;
+        if (slot % CHUNK == 0) mbar_wait(bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+        if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
+        const int bs = bcount % SB;
+        if ((slot & 1) == 0) mbar_wait(bar_b_full(bs), (bcount / SB) & 1);
+        const int as = acount % A_SLOTS;
+        mbar_wait(bar_a_full(as), (acount / A_SLOTS) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
+          const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
+          const uint64_t b_hi = make_smem_desc_sw128(base + L::B_HI + bs * L::B_PLANE_BYTES) + koff;
+          const uint64_t b_lo = make_smem_desc_sw128(base + L::B_LO + bs * L::B_PLANE_BYTES) + koff;
+          const uint32_t tmem_main = tmem_base + buf * BLOCK_N;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {                                      // two K = 16 steps per slot
+            umma_f16_ts(tmem_cross, a_lo + 8 * k, b_hi + 2 * k, idesc, (slot > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_cross, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+            umma_f16_ts(tmem_main, a_hi + 8 * k, b_hi + 2 * k, idesc, (slot % CHUNK > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_a_empty(as));
+          if ((slot & 1) || last) umma_commit(bar_b_empty(bs));
+          if (slot % CHUNK == CHUNK - 1 || last) umma_commit(bar_main_full(buf));
+          if (last) umma_commit(bar_cross_full);
+        }
+        __syncwarp();
+        ++acount;
+        if ((slot & 1) || last) ++bcount;
+        if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
+      }
+    }
+  } else if (warp < 6) {
+    // ================= A producers: gather -> split -> TMEM ==========================================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int u4 = lane & 3, rsub = lane >> 2;
+    const bool wide = p.wide_loads != 0;
+    const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
+    // row state of the tile the gather is currently in: rows 32q + 16g + rsub + 8h  (r = 2g + h)
+    const float* rbase[4];
+    int riy[4], rix[4];
+    uint32_t cur_tl = 0xffffffffu;
+    auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
+      uint32_t tl, slot;
+      p.d_slots.divmod(item, tl, slot);
+      if (tl != cur_tl) {
+        cur_tl = tl;
+        const uint32_t tile = blockIdx.x + tl * gridDim.x;
+        const int m0 = (int)p.d_tiles_n.div(tile) * BLOCK_M;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
+          uint32_t img, rem, oy, ox;
+          p.d_ohow.divmod((uint32_t)(m < p.M ? m : 0), img, rem);
+          p.d_ow.divmod(rem, oy, ox);
+          riy[r] = m < p.M ? (int)oy * p.sh - p.pt : -(1 << 28);      // a row past M never passes the bounds test
+          rix[r] = (int)ox * p.sw - p.pl;
+          rbase[r] = x + ((long long)((int)img * p.h + riy[r]) * p.w + rix[r]) * p.x_ld;
+        }
+      }
+      const uint32_t unit = slot * 4 + u4;
+      uint32_t tap, cu, ky, kx;
+      p.d_upt.divmod(unit, tap, cu);
+      p.d_kw.divmod(tap, ky, kx);
+      const bool uvalid = unit < (uint32_t)p.units;
+      const int off = ((int)ky * p.w + (int)kx) * p.x_ld + (int)cu * 8;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
+        dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, wide);
+      }
+    };
+    auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
+      const int as = item % A_SLOTS;
+      mbar_wait(bar_a_empty(as), ((item / A_SLOTS) & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t v[16];
+        const Run8& r0 = src[2 * g];               // lane rsub
+        const Run8& r1 = src[2 * g + 1];           // lane rsub + 8
+        split_pair(r0.v[0], r0.v[1], v[0], v[8]);
+        split_pair(r0.v[2], r0.v[3], v[1], v[9]);
+        split_pair(r1.v[0], r1.v[1], v[2], v[10]);
+        split_pair(r1.v[2], r1.v[3], v[3], v[11]);
+        split_pair(r0.v[4], r0.v[5], v[4], v[12]);
+        split_pair(r0.v[6], r0.v[7], v[5], v[13]);
+        split_pair(r1.v[4], r1.v[5], v[6], v[14]);
+        split_pair(r1.v[6], r1.v[7], v[7], v[15]);
+        tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
+      }
+    };
+    auto publish = [&](uint32_t item) {
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a_full(item % A_SLOTS));
+    };
+    Run8 ring[3][4];
+    if (total_items > 0) issue_loads(0, ring[0]);
+    if (total_items > 1) issue_loads(1, ring[1]);
+    if (total_items > 2) issue_loads(2, ring[2]);
+    for (uint32_t item = 0; item < total_items; item += 3) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (item + j < total_items) {
+          convert_store(item + j, ring[j]);
+          if (item + j + 3 < total_items) issue_loads(item + j + 3, ring[j]);   // refill the freed registers
+          publish(item + j);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue ======================================================================
+    const int q = warp & 3;
+    const int e = tid - (NUM_THREADS - NUM_EPILOGUE);          // 0..127
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    float* sbias = reinterpret_cast<float*>(base_ptr + L::BIAS);
+    const uint32_t stage_u32 = base + L::STAGING + q * (BLOCK_N / 32) * 4096;
+    uint8_t* stage_ptr = base_ptr + L::STAGING + q * (BLOCK_N / 32) * 4096;
+    uint32_t chunkcount = 0;
+    unsigned int bad = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
+      uint32_t m_blk, n_blk;
+      p.d_tiles_n.divmod(tile, m_blk, n_blk);
+      const int m0 = (int)m_blk * BLOCK_M, n0 = (int)n_blk * BLOCK_N;
+      named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);                 // everyone is done with the previous tile's bias
+      if (e < BLOCK_N) sbias[e] = (bias != nullptr && n0 + e < p.cout) ? __ldg(bias + n0 + e) : 0.f;
+      named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);
+      float acc[BLOCK_N];
+#pragma unroll
+      for (int j = 0; j < BLOCK_N; ++j) acc[j] = 0.f;
+      const int num_chunks = (p.num_slots + CHUNK - 1) / CHUNK;
+      for (int c = 0; c < num_chunks; ++c, ++chunkcount) {
+        const int buf = chunkcount & 1;
+        mbar_wait(bar_main_full(buf), (chunkcount >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_lane + buf * BLOCK_N + qb * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[qb * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_main_empty(buf));
+      }
+      mbar_wait(bar_cross_full, tl & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_lane + 2 * BLOCK_N + qb * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[qb * 32 + j] = fmaf(__uint_as_float(v[j]), LO_UNSCALE, acc[qb * 32 + j]);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_cross_empty);
+      // bias + activation, staged in shared memory in the 128B-swizzled box layout TMA expects
+      if (lane == 0) tma_store_wait_read();                      // the previous tile's stores have read the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + qb * 32 + c4 * 4);
+          float4 o;
+          o.x = acc[qb * 32 + c4 * 4 + 0] + b4.x; o.y = acc[qb * 32 + c4 * 4 + 1] + b4.y;
+          o.z = acc[qb * 32 + c4 * 4 + 2] + b4.z; o.w = acc[qb * 32 + c4 * 4 + 3] + b4.w;
+          bad |= ((__float_as_uint(o.x) << 1) >= 0xff000000u) | ((__float_as_uint(o.y) << 1) >= 0xff000000u) |
+                 ((__float_as_uint(o.z) << 1) >= 0xff000000u) | ((__float_as_uint(o.w) << 1) >= 0xff000000u);
+          switch (p.act) {
+            case B200OV_ACT_RELU:
+              o.x = act_t<B200OV_ACT_RELU>(o.x, 0.f, 0.f); o.y = act_t<B200OV_ACT_RELU>(o.y, 0.f, 0.f);
+              o.z = act_t<B200OV_ACT_RELU>(o.z, 0.f, 0.f); o.w = act_t<B200OV_ACT_RELU>(o.w, 0.f, 0.f);
+              break;
+            case B200OV_ACT_CLAMP:
+              o.x = act_t<B200OV_ACT_CLAMP>(o.x, p.lo, p.hi); o.y = act_t<B200OV_ACT_CLAMP>(o.y, p.lo, p.hi);
+              o.z = act_t<B200OV_ACT_CLAMP>(o.z, p.lo, p.hi); o.w = act_t<B200OV_ACT_CLAMP>(o.w, p.lo, p.hi);
+              break;
+            case B200OV_ACT_SIGMOID:
+              o.x = act_t<B200OV_ACT_SIGMOID>(o.x, 0.f, 0.f); o.y = act_t<B200OV_ACT_SIGMOID>(o.y, 0.f, 0.f);
+              o.z = act_t<B200OV_ACT_SIGMOID>(o.z, 0.f, 0.f); o.w = act_t<B200OV_ACT_SIGMOID>(o.w, 0.f, 0.f);
+              break;
+            default: break;
+          }
+          *reinterpret_cast<float4*>(stage_ptr + qb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
+        }
+      }
+      if (p.tma_store) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int qb = 0; qb < BLOCK_N / 32; ++qb)
+            if (n0 + qb * 32 < p.cout && m0 + 32 * q < p.M) tma_store_2d(&map_y, stage_u32 + qb * 4096, n0 + qb * 32, m0 + 32 * q);
+          tma_store_commit();
+        }
+      } else {
+        // pitch or alignment TMA cannot express: coalesced copy, lane = channel
+        __syncwarp();
+#pragma unroll
+        for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
+          const int n = n0 + qb * 32 + lane;
+          for (int r = 0; r < 32; ++r) {
+            const int m = m0 + 32 * q + r;
+            const float v = *reinterpret_cast<const float*>(stage_ptr + qb * 4096 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            if (m < p.M && n < p.cout) y[(long long)m * p.y_ld + n] = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (bad != 0 && status != nullptr) atomicOr(status, 1u);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// OIHW -> [plane hi | plane lo], each [coutp][kpad] halfs, K ordered (slot, kappa) with the in-slot permutation
+// the A producers use: kappa = 16*b + 4*u + j  <->  unit 4*slot + u, channel 4*b + j of that unit.
+__global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int kh,
+                                        int kw, int coutp, int kpad, int upt, int units) {
+  const long long plane = (long long)coutp * kpad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < plane;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / kpad);
+    const int kp = (int)(idx - (long long)n * kpad);
+    const int slot = kp >> 5, kappa = kp & 31;
+    const int unit = slot * 4 + ((kappa & 15) >> 2);
+    const int cj = ((kappa >> 4) << 2) + (kappa & 3);
+    float v = 0.f;
+    if (n < cout && unit < units) {
+      const int tap = unit / upt, c = (unit - tap * upt) * 8 + cj;
+      if (c < cin) {
+        const int ky = tap / kw, kx = tap - ky * kw;
+        v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+      }
+    }
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
+    out[idx] = h;
+    out[plane + idx] = l;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* ptr, long long dim0, long long dim1,
+                       long long stride1_bytes, int box0, int box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return set_error(B200OV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)stride1_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  (void)esize;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200OV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B200OV_OK;
+}
+
+template <int BLOCK_N, int SB>
+static int launch(const Params& p, const float* x, const float* bias, float* y, unsigned int* status, const CUtensorMap& mh,
+                  const CUtensorMap& ml, const CUtensorMap& my, cudaStream_t s) {
+  using L = Smem<BLOCK_N, SB>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB>;
+  static bool configured = false;
+  if (!configured) {
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int grid = p.num_tiles < props().sm_count ? p.num_tiles : props().sm_count;
+  kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(p, x, bias, y, status, mh, ml, my);
+  B200OV_LAUNCH_CHECK("conv_f16x2_kernel");
+  return B200OV_OK;
+}
+
+__device__ unsigned int g_status_word;     // sticky: bit 0 = a non-finite value left an f16x2 contraction
+
+}  // namespace f16
+
+void f16_weight_dims(int cout, int cin, int kh, int kw, int* coutp, int* kpad, int* upt, int* units) {
+  const int u = ceil_div(cin, 8);
+  const int n_units = kh * kw * u;
+  if (coutp) *coutp = round_up(cout, 8);
+  if (kpad) *kpad = round_up(n_units, 8) * 8;         // whole B stages of 64 K-elements
+  if (upt) *upt = u;
+  if (units) *units = n_units;
+}
+
+long long f16_section_floats(int cout, int cin, int kh, int kw) {
+  int coutp, kpad;
+  f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, nullptr, nullptr);
+  return (long long)coutp * kpad;                     // two planes of halfs
+}
+
+int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s) {
+  int coutp, kpad, upt, units;
+  f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, &upt, &units);
+  f16::pack_f16_weights_kernel<<<bw_grid((long long)coutp * kpad, 256), 256, 0, s>>>(w_oihw, reinterpret_cast<__half*>(out), cout,
+                                                                                    cin, kh, kw, coutp, kpad, upt, units);
+  B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
+  return B200OV_OK;
+}
+
+// The gather reads whole 8-channel runs: either cin is a multiple of 8, or the pixel pitch covers the padded
+// run (x_ld >= round_up(cin, 8); the producer of x zero-fills the pad lanes, e.g. the network-input layout kernel).
+bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
+  return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || d->x_ld >= round_up(d->cin, 8));
+}
+
+unsigned int* f16x2_status_word() {
+  unsigned int* p = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&p), f16::g_status_word) != cudaSuccess) return nullptr;
+  return p;
+}
+
+// `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.
+int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
+  if (!f16x2_eligible(d, x))
+    return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with 8-channel runs (cin %% 8 == 0 or x_ld >= cin padded to 8)");
+  f16::Params p;
+  memset(&p, 0, sizeof(p));
+  p.h = d->h; p.w = d->w; p.cin = d->cin; p.cout = d->cout; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.pl = d->pl;
+  p.x_ld = d->x_ld; p.y_ld = d->y_ld;
+  const long long M = (long long)d->n * d->oh * d->ow;
+  if (M > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: too many output pixels");
+  p.M = (int)M;
+  if (p.M == 0) return B200OV_OK;
+  int coutp, kpad, upt, units;
+  f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
+  p.units = units;
+  p.num_slots = ceil_div(units, 4);
+  const int block_n = d->cout > 64 ? 128 : (d->cout > 32 ? 64 : 32);
+  p.tiles_n = ceil_div(d->cout, block_n);
+  const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n;
+  if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
+  p.num_tiles = (int)tiles;
+  p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
+  p.tma_store = (d->y_ld % 4 == 0) && aligned16(y);
+  p.wide_loads = (d->x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
+  p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(d->kw);
+  p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
+  const __half* hi_plane = reinterpret_cast<const __half*>(wt);
+  const __half* lo_plane = hi_plane + (long long)coutp * kpad;
+  CUtensorMap mh, ml, my;
+  int rc = f16::make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
+  if (rc) return rc;
+  rc = f16::make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
+  if (rc) return rc;
+  if (p.tma_store) {
+    rc = f16::make_map_2d(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, d->cout, p.M, (long long)d->y_ld * 4, 32, 32);
+    if (rc) return rc;
+  } else {
+    my = mh;       // never dereferenced
+  }
+  unsigned int* status = f16x2_status_word();
+  if (block_n == 128) return f16::launch<128, 4>(p, x, bias, y, status, mh, ml, my, s);
+  if (block_n == 64) return f16::launch<64, 4>(p, x, bias, y, status, mh, ml, my, s);
+  return f16::launch<32, 4>(p, x, bias, y, status, mh, ml, my, s);
+}
+
+}  // namespace b200ov

@@ -260,7 +260,9 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
 namespace b200ov {
 void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* kpad);
 int pack_tf32_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s);
-static bool has_tf32_section(int cin) { return cin % 4 == 0 && cin >= 8; }
+bool has_tf32_section(int cin) { return cin % 4 == 0 && cin >= 8; }
+long long f16_section_floats(int cout, int cin, int kh, int kw);
+int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s);
 }  // namespace b200ov
 
 using namespace b200ov;
@@ -280,6 +282,7 @@ int b200ov_conv_weight_dims(int cout, int cin, int kh, int kw, int* rows, int* l
       tf32_weight_dims(cout, cin, kh, kw, &coutp, &kpad);
       total += 2LL * coutp * kpad;
     }
+    total += f16_section_floats(cout, cin, kh, kw);
     *total_floats = total;
   }
   return B200OV_OK;
@@ -294,8 +297,15 @@ int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int
   pack_conv_weights_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_oihw, w_packed, cout, cin, kh, kw,
                                                                               kh * kw * cin, rows, ldw);
   B200OV_LAUNCH_CHECK("pack_conv_weights_kernel");
-  if (has_tf32_section(cin)) return pack_tf32_weights(w_oihw, w_packed + total, cout, cin, kh, kw, as_stream(stream));
-  return B200OV_OK;
+  if (has_tf32_section(cin)) {
+    rc = pack_tf32_weights(w_oihw, w_packed + total, cout, cin, kh, kw, as_stream(stream));
+    if (rc) return rc;
+    int coutp;
+    long long kpad;
+    tf32_weight_dims(cout, cin, kh, kw, &coutp, &kpad);
+    total += 2LL * coutp * kpad;
+  }
+  return pack_f16_weights(w_oihw, w_packed + total, cout, cin, kh, kw, as_stream(stream));
 }
 
 }  // extern "C"

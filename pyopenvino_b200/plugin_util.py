@@ -15,7 +15,7 @@ dtype / shape validation first.  Extensions, all optional and ignored by referen
 from . import _cabi, common_def
 from .device import is_device
 
-_MATH = {'fp32': _cabi.MATH_FP32, 'tf32x3': _cabi.MATH_TF32X3, 'tf32': _cabi.MATH_TF32}
+_MATH = {'fp32': _cabi.MATH_FP32, 'tf32x3': _cabi.MATH_TF32X3, 'tf32': _cabi.MATH_TF32, 'f16x2': _cabi.MATH_F16X2}
 
 
 def math_mode(kernel_type):
