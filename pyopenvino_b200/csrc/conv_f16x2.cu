@@ -13,17 +13,18 @@
 // GEMM view (reference: Convolution.py:57-87):  D[M pixels][N cout] = A[M][K] * W[N][K]^T.  K is cut into
 // units of 8 channels of one filter tap (cin padded to 8), 4 units = one 32-wide "slot".
 //
-// Warp roles (320 threads, one persistent CTA per SM, static round-robin tile schedule):
+// Warp roles (512 threads = 4 warpgroups with setmaxnreg budgets, one persistent CTA per SM, static tile schedule):
 //   warp 0      B loader : TMA loads of the pre-split FP16 weight tiles (hi / lo planes, 64 K-elements per
 //                          stage, 128B swizzle) into a shared-memory ring.
 //   warp 1      MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
 //                          shared memory; tcgen05.commit releases A slots / B stages / accumulators.
-//   warps 2-5   A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
-//                          4 threads cover one pixel's 32-channel run, software-pipelined 3 slots deep, running
-//                          ahead across tile boundaries), FP32 -> FP16 hi/lo split with packed FP32 math, and
-//                          tcgen05.st into a 4-slot TMEM ring.  The A operand never touches shared memory: the
-//                          MMA reads of B alone already use ~60% of the 128 B/clk shared-memory port.
-//   warps 6-9   epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
+//   warps 4-11  A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
+//                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split with packed
+//                          FP32 math, and tcgen05.st into a 4-slot TMEM ring.  Two sets of four warps work on
+//                          alternating pairs of slots, running ahead across tile boundaries.  The A operand
+//                          never touches shared memory: the MMA reads of B alone already use ~60% of the
+//                          128 B/clk shared-memory port.
+//   warps 12-15 epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
 //                          see below), add the cross terms, bias, activation, stage the tile in shared memory
 //                          and write it with TMA stores (coalesced, asynchronous), overlapping the next tile.
 //
@@ -50,9 +51,12 @@ constexpr int A_SLOTS = 4;             // TMEM ring depth
 constexpr int A_COL0 = 384;            // TMEM columns [384, 512): A ring, 32 columns per slot (16 hi + 16 lo)
 constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
 constexpr int CHUNK = 2;               // slots per promotion chunk (64 K elements)
-constexpr int NUM_THREADS = 320;
-constexpr int NUM_PRODUCERS = 128;
+constexpr int NUM_SETS = 2;             // producer warp sets
+constexpr int SET_THREADS = 128;       // threads that build one A slot
 constexpr int NUM_EPILOGUE = 128;
+constexpr int NUM_THREADS = 128 + NUM_SETS * SET_THREADS + NUM_EPILOGUE;      // 512: four warpgroups
+// register budget per warpgroup (setmaxnreg): 40 + 2 * 136 + 200 = 512 = 4 * 128 (the launch allocation)
+constexpr int REGS_CONTROL = 40, REGS_PRODUCER = 136, REGS_EPILOGUE = 200;
 constexpr int EPI_BAR_ID = 1;
 constexpr float LO_SCALE = 2048.f;     // 2^11
 constexpr float LO_UNSCALE = 1.f / 2048.f;
@@ -74,8 +78,9 @@ struct Smem {
   static constexpr int B_PLANE_BYTES = BLOCK_N * 128;                  // one stage of one plane: BLOCK_N rows x 64 halfs
   static constexpr int B_HI = 0;
   static constexpr int B_LO = B_HI + SB * B_PLANE_BYTES;
-  static constexpr int STAGING = B_LO + SB * B_PLANE_BYTES;            // 4 warps x (BLOCK_N / 32) blocks x 4 KB
-  static constexpr int STAGING_BYTES = 4 * (BLOCK_N / 32) * 4096;
+  static constexpr int STG_BLOCKS = BLOCK_N >= 64 ? 2 : 1;            // 32-column blocks staged per round
+  static constexpr int STAGING = B_LO + SB * B_PLANE_BYTES;            // 4 warps x STG_BLOCKS blocks x 4 KB
+  static constexpr int STAGING_BYTES = 4 * STG_BLOCKS * 4096;
   static constexpr int BIAS = STAGING + STAGING_BYTES;                 // BLOCK_N floats
   static constexpr int BARS = BIAS + BLOCK_N * 4;
   // b_full[SB], b_empty[SB], a_full[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full, cross_empty
@@ -103,6 +108,16 @@ __device__ __forceinline__ float2 unpack_f32x2(f32x2 v) {
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 pack_u32x2(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
@@ -139,15 +154,7 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
   return r;
 }
 
-template <int ACT>
-__device__ __forceinline__ float act_t(float v, float lo, float hi) {
-  if constexpr (ACT == B200OV_ACT_RELU) return v < 0.f ? 0.f : v;
-  else if constexpr (ACT == B200OV_ACT_CLAMP) return fminf(fmaxf(v, lo), hi);
-  else if constexpr (ACT == B200OV_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
-  else return v;
-}
-
-template <int BLOCK_N, int SB>
+template <int BLOCK_N, int SB, bool WIDE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
@@ -175,7 +182,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       mbar_init(bar_b_empty(s), 1);
     }
     for (int s = 0; s < A_SLOTS; ++s) {
-      mbar_init(bar_a_full(s), NUM_PRODUCERS);
+      mbar_init(bar_a_full(s), SET_THREADS);
       mbar_init(bar_a_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -198,66 +205,75 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
   const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int num_stages = (p.num_slots + 1) >> 1;      // B stages per tile
 
-  if (warp == 0) {
-    // ================= B loader ======================================================================
-    if (lane == 0) {
-      uint32_t bcount = 0;
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
-        const int n0 = (int)(tile - p.d_tiles_n.div(tile) * p.d_tiles_n.d) * BLOCK_N;
-        for (int ks = 0; ks < num_stages; ++ks, ++bcount) {
-          const int s = bcount % SB;
-          mbar_wait(bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_b_full(s), 2 * L::B_PLANE_BYTES);
-          tma_load_2d(base + L::B_HI + s * L::B_PLANE_BYTES, &map_hi, ks * STAGE_K, n0, bar_b_full(s));
-          tma_load_2d(base + L::B_LO + s * L::B_PLANE_BYTES, &map_lo, ks * STAGE_K, n0, bar_b_full(s));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer ====================================================================
-    constexpr uint32_t idesc = instr_desc(BLOCK_N);
-    const uint32_t tmem_cross = tmem_base + 2 * BLOCK_N;
-    uint32_t acount = 0, bcount = 0, chunkcount = 0;
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      for (int slot = 0; slot < p.num_slots; ++slot) {
-        const bool last = slot == p.num_slots - 1;
-        const int buf = chunkcount & 1;
-        if (slot % CHUNK == 0) mbar_wait(bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
-        if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
-        const int bs = bcount % SB;
-        if ((slot & 1) == 0) mbar_wait(bar_b_full(bs), (bcount / SB) & 1);
-        const int as = acount % A_SLOTS;
-        mbar_wait(bar_a_full(as), (acount / A_SLOTS) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
-          const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
-          const uint64_t b_hi = make_smem_desc_sw128(base + L::B_HI + bs * L::B_PLANE_BYTES) + koff;
-          const uint64_t b_lo = make_smem_desc_sw128(base + L::B_LO + bs * L::B_PLANE_BYTES) + koff;
-          const uint32_t tmem_main = tmem_base + buf * BLOCK_N;
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {                                      // two K = 16 steps per slot
-            umma_f16_ts(tmem_cross, a_lo + 8 * k, b_hi + 2 * k, idesc, (slot > 0 || k > 0) ? 1u : 0u);
-            umma_f16_ts(tmem_cross, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
-            umma_f16_ts(tmem_main, a_hi + 8 * k, b_hi + 2 * k, idesc, (slot % CHUNK > 0 || k > 0) ? 1u : 0u);
+  if (warp < 4) {
+    // warpgroup 0: B loader (warp 0), MMA issuer (warp 1), two idle warps.  Hand the registers to the others.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+    if (warp == 0) {
+      // ================= B loader ====================================================================
+      if (lane == 0) {
+        uint32_t bcount = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+          const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
+          const int n0 = (int)(tile - p.d_tiles_n.div(tile) * p.d_tiles_n.d) * BLOCK_N;
+          for (int ks = 0; ks < num_stages; ++ks, ++bcount) {
+            const int s = bcount % SB;
+            mbar_wait(bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_b_full(s), 2 * L::B_PLANE_BYTES);
+            tma_load_2d(base + L::B_HI + s * L::B_PLANE_BYTES, &map_hi, ks * STAGE_K, n0, bar_b_full(s));
+            tma_load_2d(base + L::B_LO + s * L::B_PLANE_BYTES, &map_lo, ks * STAGE_K, n0, bar_b_full(s));
           }
-          umma_commit(bar_a_empty(as));
-          if ((slot & 1) || last) umma_commit(bar_b_empty(bs));
-          if (slot % CHUNK == CHUNK - 1 || last) umma_commit(bar_main_full(buf));
-          if (last) umma_commit(bar_cross_full);
         }
-        __syncwarp();
-        ++acount;
-        if ((slot & 1) || last) ++bcount;
-        if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
+      }
+    } else if (warp == 1) {
+      // ================= MMA issuer ==================================================================
+      constexpr uint32_t idesc = instr_desc(BLOCK_N);
+      const uint32_t tmem_cross = tmem_base + 2 * BLOCK_N;
+      uint32_t acount = 0, bcount = 0, chunkcount = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int slot = 0; slot < p.num_slots; ++slot) {
+          const bool last = slot == p.num_slots - 1;
+          const int buf = chunkcount & 1;
+          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+          if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
+          const int bs = bcount % SB;
+          if ((slot & 1) == 0) mbar_wait(bar_b_full(bs), (bcount / SB) & 1);
+          const int as = acount % A_SLOTS;
+          mbar_wait(bar_a_full(as), (acount / A_SLOTS) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
+            const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
+            const uint64_t b_hi = make_smem_desc_sw128(base + L::B_HI + bs * L::B_PLANE_BYTES) + koff;
+            const uint64_t b_lo = make_smem_desc_sw128(base + L::B_LO + bs * L::B_PLANE_BYTES) + koff;
+            const uint32_t tmem_main = tmem_base + buf * BLOCK_N;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {                                      // two K = 16 steps per slot
+              umma_f16_ts(tmem_main, a_hi + 8 * k, b_hi + 2 * k, idesc, (slot % CHUNK > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ts(tmem_cross, a_lo + 8 * k, b_hi + 2 * k, idesc, (slot > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ts(tmem_cross, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+            }
+            umma_commit(bar_a_empty(as));
+            if ((slot & 1) || last) umma_commit(bar_b_empty(bs));
+            if (slot % CHUNK == CHUNK - 1 || last) umma_commit(bar_main_full(buf));
+            if (last) umma_commit(bar_cross_full);
+          }
+          __syncwarp();
+          ++acount;
+          if ((slot & 1) || last) ++bcount;
+          if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
+        }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 4 + 4 * NUM_SETS) {
     // ================= A producers: gather -> split -> TMEM ==========================================
+    // Two sets of four warps; a set owns every other PAIR of consecutive slots ("items").  All loads of a
+    // warp share one scoreboard slot, so a register ring inside a warp cannot overlap load latency with
+    // the split; the overlap comes from the other set (and the other warps of the SM sub-partition)
+    // working on the neighbouring pair in the meantime.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    const int set = (warp - 4) >> 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int u4 = lane & 3, rsub = lane >> 2;
-    const bool wide = p.wide_loads != 0;
     const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
     // row state of the tile the gather is currently in: rows 32q + 16g + rsub + 8h  (r = 2g + h)
     const float* rbase[4];
@@ -290,7 +306,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
-        dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, wide);
+        dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, WIDE);
       }
     };
     auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
@@ -312,36 +328,31 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         split_pair(r1.v[6], r1.v[7], v[7], v[15]);
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
-    };
-    auto publish = [&](uint32_t item) {
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_a_full(item % A_SLOTS));
+      mbar_arrive(bar_a_full(as));
     };
-    Run8 ring[3][4];
-    if (total_items > 0) issue_loads(0, ring[0]);
-    if (total_items > 1) issue_loads(1, ring[1]);
-    if (total_items > 2) issue_loads(2, ring[2]);
-    for (uint32_t item = 0; item < total_items; item += 3) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (item + j < total_items) {
-          convert_store(item + j, ring[j]);
-          if (item + j + 3 < total_items) issue_loads(item + j + 3, ring[j]);   // refill the freed registers
-          publish(item + j);
-        }
-      }
+    Run8 d0[4], d1[4];
+    for (uint32_t item = 2 * set; item < total_items; item += 2 * NUM_SETS) {
+      const bool two = item + 1 < total_items;
+      issue_loads(item, d0);
+      if (two) issue_loads(item + 1, d1);
+      convert_store(item, d0);
+      if (two) convert_store(item + 1, d1);
     }
   } else {
     // ================= epilogue ======================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
     const int q = warp & 3;
     const int e = tid - (NUM_THREADS - NUM_EPILOGUE);          // 0..127
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * q) << 16);
     float* sbias = reinterpret_cast<float*>(base_ptr + L::BIAS);
-    const uint32_t stage_u32 = base + L::STAGING + q * (BLOCK_N / 32) * 4096;
-    uint8_t* stage_ptr = base_ptr + L::STAGING + q * (BLOCK_N / 32) * 4096;
+    const uint32_t stage_u32 = base + L::STAGING + q * L::STG_BLOCKS * 4096;
+    uint8_t* stage_ptr = base_ptr + L::STAGING + q * L::STG_BLOCKS * 4096;
     uint32_t chunkcount = 0;
-    unsigned int bad = 0;
+    f32x2 chk = pack_f32x2(0.f, 0.f);
+    const float act_lo = p.act == B200OV_ACT_NONE ? -INFINITY : (p.act == B200OV_ACT_RELU ? 0.f : p.lo);
+    const float act_hi = p.act == B200OV_ACT_CLAMP ? p.hi : INFINITY;
     for (int tl = 0; tl < my_tiles; ++tl) {
       const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
       uint32_t m_blk, n_blk;
@@ -350,11 +361,16 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);                 // everyone is done with the previous tile's bias
       if (e < BLOCK_N) sbias[e] = (bias != nullptr && n0 + e < p.cout) ? __ldg(bias + n0 + e) : 0.f;
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);
-      float acc[BLOCK_N];
+      // FP32 accumulators as packed pairs (FADD2 / FFMA2 halve the issue slots), initialised with the bias
+      f32x2 acc[BLOCK_N / 2];
 #pragma unroll
-      for (int j = 0; j < BLOCK_N; ++j) acc[j] = 0.f;
+      for (int j = 0; j < BLOCK_N / 4; ++j) {
+        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(sbias + 4 * j);
+        acc[2 * j] = b4.x;
+        acc[2 * j + 1] = b4.y;
+      }
       const int num_chunks = (p.num_slots + CHUNK - 1) / CHUNK;
-      for (int c = 0; c < num_chunks; ++c, ++chunkcount) {
+      auto promote = [&]() {
         const int buf = chunkcount & 1;
         mbar_wait(bar_main_full(buf), (chunkcount >> 1) & 1);
         tc_fence_after();
@@ -363,79 +379,81 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_lane + buf * BLOCK_N + qb * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[qb * 32 + j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) acc[qb * 16 + j] = add2(acc[qb * 16 + j], pack_u32x2(v[2 * j], v[2 * j + 1]));
         }
         tc_fence_before();
         mbar_arrive(bar_main_empty(buf));
-      }
+        ++chunkcount;
+      };
+      for (int c = 0; c < num_chunks - 1; ++c) promote();
+      // The cross terms are complete together with the last chunk: read them first so the MMA warp can start
+      // the next tile's cross accumulation while the last chunk is still being promoted.
       mbar_wait(bar_cross_full, tl & 1);
       tc_fence_after();
+      const f32x2 unscale = pack_f32x2(LO_UNSCALE, LO_UNSCALE);
 #pragma unroll
       for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_lane + 2 * BLOCK_N + qb * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[qb * 32 + j] = fmaf(__uint_as_float(v[j]), LO_UNSCALE, acc[qb * 32 + j]);
+        for (int j = 0; j < 16; ++j) acc[qb * 16 + j] = fma2(pack_u32x2(v[2 * j], v[2 * j + 1]), unscale, acc[qb * 16 + j]);
       }
       tc_fence_before();
       mbar_arrive(bar_cross_empty);
-      // bias + activation, staged in shared memory in the 128B-swizzled box layout TMA expects
-      if (lane == 0) tma_store_wait_read();                      // the previous tile's stores have read the staging buffer
-      __syncwarp();
+      promote();
+      // activation (None / ReLU / Clamp as one clamp with infinite bounds), staged in shared memory in the
+      // 128B-swizzled box layout TMA expects, STG_BLOCKS 32-column blocks per round.  chk turns NaN as soon
+      // as one output is inf / NaN.
+      const f32x2 zero2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
-      for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sbias + qb * 32 + c4 * 4);
-          float4 o;
-          o.x = acc[qb * 32 + c4 * 4 + 0] + b4.x; o.y = acc[qb * 32 + c4 * 4 + 1] + b4.y;
-          o.z = acc[qb * 32 + c4 * 4 + 2] + b4.z; o.w = acc[qb * 32 + c4 * 4 + 3] + b4.w;
-          bad |= ((__float_as_uint(o.x) << 1) >= 0xff000000u) | ((__float_as_uint(o.y) << 1) >= 0xff000000u) |
-                 ((__float_as_uint(o.z) << 1) >= 0xff000000u) | ((__float_as_uint(o.w) << 1) >= 0xff000000u);
-          switch (p.act) {
-            case B200OV_ACT_RELU:
-              o.x = act_t<B200OV_ACT_RELU>(o.x, 0.f, 0.f); o.y = act_t<B200OV_ACT_RELU>(o.y, 0.f, 0.f);
-              o.z = act_t<B200OV_ACT_RELU>(o.z, 0.f, 0.f); o.w = act_t<B200OV_ACT_RELU>(o.w, 0.f, 0.f);
-              break;
-            case B200OV_ACT_CLAMP:
-              o.x = act_t<B200OV_ACT_CLAMP>(o.x, p.lo, p.hi); o.y = act_t<B200OV_ACT_CLAMP>(o.y, p.lo, p.hi);
-              o.z = act_t<B200OV_ACT_CLAMP>(o.z, p.lo, p.hi); o.w = act_t<B200OV_ACT_CLAMP>(o.w, p.lo, p.hi);
-              break;
-            case B200OV_ACT_SIGMOID:
-              o.x = act_t<B200OV_ACT_SIGMOID>(o.x, 0.f, 0.f); o.y = act_t<B200OV_ACT_SIGMOID>(o.y, 0.f, 0.f);
-              o.z = act_t<B200OV_ACT_SIGMOID>(o.z, 0.f, 0.f); o.w = act_t<B200OV_ACT_SIGMOID>(o.w, 0.f, 0.f);
-              break;
-            default: break;
-          }
-          *reinterpret_cast<float4*>(stage_ptr + qb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
-        }
-      }
-      if (p.tma_store) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int qb = 0; qb < BLOCK_N / 32; ++qb)
-            if (n0 + qb * 32 < p.cout && m0 + 32 * q < p.M) tma_store_2d(&map_y, stage_u32 + qb * 4096, n0 + qb * 32, m0 + 32 * q);
-          tma_store_commit();
-        }
-      } else {
-        // pitch or alignment TMA cannot express: coalesced copy, lane = channel
+      for (int round = 0; round < (BLOCK_N / 32) / L::STG_BLOCKS; ++round) {
+        if (lane == 0) tma_store_wait_read();                    // earlier stores have read the staging buffer
         __syncwarp();
 #pragma unroll
-        for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
-          const int n = n0 + qb * 32 + lane;
-          for (int r = 0; r < 32; ++r) {
-            const int m = m0 + 32 * q + r;
-            const float v = *reinterpret_cast<const float*>(stage_ptr + qb * 4096 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-            if (m < p.M && n < p.cout) y[(long long)m * p.y_ld + n] = v;
+        for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
+          const int qb = round * L::STG_BLOCKS + sb;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const f32x2 a0 = acc[qb * 16 + c4 * 2], a1 = acc[qb * 16 + c4 * 2 + 1];
+            chk = fma2(a0, zero2, chk);
+            chk = fma2(a1, zero2, chk);
+            const float2 u0 = unpack_f32x2(a0), u1 = unpack_f32x2(a1);
+            float4 o;
+            o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
+            o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
+            *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
           }
         }
-        __syncwarp();
+        if (p.tma_store) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
+              const int nb = n0 + (round * L::STG_BLOCKS + sb) * 32;
+              if (nb < p.cout && m0 + 32 * q < p.M) tma_store_2d(&map_y, stage_u32 + sb * 4096, nb, m0 + 32 * q);
+            }
+            tma_store_commit();
+          }
+        } else {
+          // pitch or alignment TMA cannot express: coalesced copy, lane = channel
+          __syncwarp();
+#pragma unroll
+          for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
+            const int n = n0 + (round * L::STG_BLOCKS + sb) * 32 + lane;
+            for (int r = 0; r < 32; ++r) {
+              const int m = m0 + 32 * q + r;
+              const float v = *reinterpret_cast<const float*>(stage_ptr + sb * 4096 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+              if (m < p.M && n < p.cout) y[(long long)m * p.y_ld + n] = v;
+            }
+          }
+          __syncwarp();
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();
-    if (bad != 0 && status != nullptr) atomicOr(status, 1u);
+    const float2 ck = unpack_f32x2(chk);
+    if ((ck.x != ck.x || ck.y != ck.y) && status != nullptr) atomicOr(status, 1u);
   }
 
   tc_fence_before();
@@ -502,11 +520,11 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
   return B200OV_OK;
 }
 
-template <int BLOCK_N, int SB>
+template <int BLOCK_N, int SB, bool WIDE>
 static int launch(const Params& p, const float* x, const float* bias, float* y, unsigned int* status, const CUtensorMap& mh,
                   const CUtensorMap& ml, const CUtensorMap& my, cudaStream_t s) {
   using L = Smem<BLOCK_N, SB>;
-  auto kern = conv_f16x2_kernel<BLOCK_N, SB>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE>;
   static bool configured = false;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -549,7 +567,8 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
 // The gather reads whole 8-channel runs: either cin is a multiple of 8, or the pixel pitch covers the padded
 // run (x_ld >= round_up(cin, 8); the producer of x zero-fills the pad lanes, e.g. the network-input layout kernel).
 bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
-  return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || d->x_ld >= round_up(d->cin, 8));
+  return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || d->x_ld >= round_up(d->cin, 8)) &&
+         d->act != B200OV_ACT_SIGMOID;
 }
 
 unsigned int* f16x2_status_word() {
@@ -561,7 +580,7 @@ unsigned int* f16x2_status_word() {
 // `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.
 int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
   if (!f16x2_eligible(d, x))
-    return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with 8-channel runs (cin %% 8 == 0 or x_ld >= cin padded to 8)");
+    return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with 8-channel runs (cin %% 8 == 0 or x_ld >= cin padded to 8) and no fused Sigmoid");
   f16::Params p;
   memset(&p, 0, sizeof(p));
   p.h = d->h; p.w = d->w; p.cin = d->cin; p.cout = d->cout; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.pl = d->pl;
@@ -598,9 +617,14 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
     my = mh;       // never dereferenced
   }
   unsigned int* status = f16x2_status_word();
-  if (block_n == 128) return f16::launch<128, 4>(p, x, bias, y, status, mh, ml, my, s);
-  if (block_n == 64) return f16::launch<64, 4>(p, x, bias, y, status, mh, ml, my, s);
-  return f16::launch<32, 4>(p, x, bias, y, status, mh, ml, my, s);
+  if (p.wide_loads) {
+    if (block_n == 128) return f16::launch<128, 3, true>(p, x, bias, y, status, mh, ml, my, s);
+    if (block_n == 64) return f16::launch<64, 4, true>(p, x, bias, y, status, mh, ml, my, s);
+    return f16::launch<32, 4, true>(p, x, bias, y, status, mh, ml, my, s);
+  }
+  if (block_n == 128) return f16::launch<128, 3, false>(p, x, bias, y, status, mh, ml, my, s);
+  if (block_n == 64) return f16::launch<64, 4, false>(p, x, bias, y, status, mh, ml, my, s);
+  return f16::launch<32, 4, false>(p, x, bias, y, status, mh, ml, my, s);
 }
 
 }  // namespace b200ov
