@@ -34,6 +34,7 @@
 // accumulator for the whole tile.  Tests hold the result to |d| <= 1e-5 + 1e-4|ref| against the oracle.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "fastdiv.cuh"
@@ -72,6 +73,20 @@ struct Params {
 };
 
 __device__ __align__(32) float g_zero_run[8];      // source of the np.pad zeros
+
+#ifdef B200OV_F16_TRACE
+// developer-only (build with B200OV_EXTRA_NVCC_FLAGS=-DB200OV_F16_TRACE): cycles CTA 0 spends in each wait, per role
+__device__ long long g_f16_trace[4][8];
+#define F16_TRACE_DECL long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start_ = clock64();
+#define F16_WAIT(k, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); tr_[k] += clock64() - t0_; } while (0)
+#define F16_TIMED(k, stmt) do { const long long t0_ = clock64(); stmt; tr_[k] += clock64() - t0_; } while (0)
+#define F16_TRACE_STORE(role, cond) do { if (blockIdx.x == 0 && (cond)) { tr_[7] = clock64() - tr_start_; for (int i_ = 0; i_ < 8; ++i_) g_f16_trace[role][i_] = tr_[i_]; } } while (0)
+#else
+#define F16_TRACE_DECL
+#define F16_WAIT(k, bar, par) mbar_wait(bar, par)
+#define F16_TIMED(k, stmt) stmt
+#define F16_TRACE_STORE(role, cond)
+#endif
 
 template <int BLOCK_N, int SB>
 struct Smem {
@@ -210,37 +225,43 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
     if (warp == 0) {
       // ================= B loader ====================================================================
-      if (lane == 0) {
+      {
+        F16_TRACE_DECL
         uint32_t bcount = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
           const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
           const int n0 = (int)(tile - p.d_tiles_n.div(tile) * p.d_tiles_n.d) * BLOCK_N;
           for (int ks = 0; ks < num_stages; ++ks, ++bcount) {
             const int s = bcount % SB;
-            mbar_wait(bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
-            mbar_arrive_expect_tx(bar_b_full(s), 2 * L::B_PLANE_BYTES);
-            tma_load_2d(base + L::B_HI + s * L::B_PLANE_BYTES, &map_hi, ks * STAGE_K, n0, bar_b_full(s));
-            tma_load_2d(base + L::B_LO + s * L::B_PLANE_BYTES, &map_lo, ks * STAGE_K, n0, bar_b_full(s));
+            F16_WAIT(0, bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(bar_b_full(s), 2 * L::B_PLANE_BYTES);
+              tma_load_2d(base + L::B_HI + s * L::B_PLANE_BYTES, &map_hi, ks * STAGE_K, n0, bar_b_full(s));
+              tma_load_2d(base + L::B_LO + s * L::B_PLANE_BYTES, &map_lo, ks * STAGE_K, n0, bar_b_full(s));
+            }
+            __syncwarp();
           }
         }
+        F16_TRACE_STORE(0, lane == 0);
       }
     } else if (warp == 1) {
       // ================= MMA issuer ==================================================================
       constexpr uint32_t idesc = instr_desc(BLOCK_N);
       const uint32_t tmem_cross = tmem_base + 2 * BLOCK_N;
       uint32_t acount = 0, bcount = 0, chunkcount = 0;
+      F16_TRACE_DECL
       for (int tl = 0; tl < my_tiles; ++tl) {
         for (int slot = 0; slot < p.num_slots; ++slot) {
           const bool last = slot == p.num_slots - 1;
           const int buf = chunkcount & 1;
-          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
-          if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
+          if (slot % CHUNK == 0) F16_WAIT(0, bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+          if (slot == 0) F16_WAIT(1, bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
           const int bs = bcount % SB;
-          if ((slot & 1) == 0) mbar_wait(bar_b_full(bs), (bcount / SB) & 1);
+          if ((slot & 1) == 0) F16_WAIT(2, bar_b_full(bs), (bcount / SB) & 1);
           const int as = acount % A_SLOTS;
-          mbar_wait(bar_a_full(as), (acount / A_SLOTS) & 1);
+          F16_WAIT(3, bar_a_full(as), (acount / A_SLOTS) & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
             const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
             const uint64_t b_hi = make_smem_desc_sw128(base + L::B_HI + bs * L::B_PLANE_BYTES) + koff;
@@ -263,6 +284,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
         }
       }
+      F16_TRACE_STORE(1, lane == 0);
     }
   } else if (warp < 4 + 4 * NUM_SETS) {
     // ================= A producers: gather -> split -> TMEM ==========================================
@@ -279,6 +301,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     const float* rbase[4];
     int riy[4], rix[4];
     uint32_t cur_tl = 0xffffffffu;
+    F16_TRACE_DECL
     auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
       uint32_t tl, slot;
       p.d_slots.divmod(item, tl, slot);
@@ -311,7 +334,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     };
     auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
       const int as = item % A_SLOTS;
-      mbar_wait(bar_a_empty(as), ((item / A_SLOTS) & 1) ^ 1);
+      F16_WAIT(0, bar_a_empty(as), ((item / A_SLOTS) & 1) ^ 1);
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -328,18 +351,18 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         split_pair(r1.v[6], r1.v[7], v[7], v[15]);
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
-      tmem_st_wait();
+      F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
       mbar_arrive(bar_a_full(as));
     };
     Run8 d0[4], d1[4];
     for (uint32_t item = 2 * set; item < total_items; item += 2 * NUM_SETS) {
       const bool two = item + 1 < total_items;
-      issue_loads(item, d0);
-      if (two) issue_loads(item + 1, d1);
-      convert_store(item, d0);
-      if (two) convert_store(item + 1, d1);
+      F16_TIMED(1, issue_loads(item, d0); if (two) issue_loads(item + 1, d1));
+      F16_TIMED(3, convert_store(item, d0));
+      if (two) F16_TIMED(4, convert_store(item + 1, d1));
     }
+    F16_TRACE_STORE(2, warp == 4 && lane == 0);
   } else {
     // ================= epilogue ======================================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
@@ -353,6 +376,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     f32x2 chk = pack_f32x2(0.f, 0.f);
     const float act_lo = p.act == B200OV_ACT_NONE ? -INFINITY : (p.act == B200OV_ACT_RELU ? 0.f : p.lo);
     const float act_hi = p.act == B200OV_ACT_CLAMP ? p.hi : INFINITY;
+    F16_TRACE_DECL
     for (int tl = 0; tl < my_tiles; ++tl) {
       const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
       uint32_t m_blk, n_blk;
@@ -372,7 +396,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       const int num_chunks = (p.num_slots + CHUNK - 1) / CHUNK;
       auto promote = [&]() {
         const int buf = chunkcount & 1;
-        mbar_wait(bar_main_full(buf), (chunkcount >> 1) & 1);
+        F16_WAIT(0, bar_main_full(buf), (chunkcount >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
@@ -388,7 +412,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       for (int c = 0; c < num_chunks - 1; ++c) promote();
       // The cross terms are complete together with the last chunk: read them first so the MMA warp can start
       // the next tile's cross accumulation while the last chunk is still being promoted.
-      mbar_wait(bar_cross_full, tl & 1);
+      F16_WAIT(1, bar_cross_full, tl & 1);
       tc_fence_after();
       const f32x2 unscale = pack_f32x2(LO_UNSCALE, LO_UNSCALE);
 #pragma unroll
@@ -407,7 +431,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       const f32x2 zero2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
       for (int round = 0; round < (BLOCK_N / 32) / L::STG_BLOCKS; ++round) {
-        if (lane == 0) tma_store_wait_read();                    // earlier stores have read the staging buffer
+        F16_TIMED(2, tma_store_wait_read());                     // this thread's earlier stores have read the staging buffer
         __syncwarp();
 #pragma unroll
         for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
@@ -427,7 +451,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         if (p.tma_store) {
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one_sync()) {
 #pragma unroll
             for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
               const int nb = n0 + (round * L::STG_BLOCKS + sb) * 32;
@@ -451,7 +475,8 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         }
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    tma_store_wait_all();
+    F16_TRACE_STORE(3, warp == 12 && lane == 0);
     const float2 ck = unpack_f32x2(chk);
     if ((ck.x != ck.x || ck.y != ck.y) && status != nullptr) atomicOr(status, 1u);
   }
@@ -571,6 +596,12 @@ bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
          d->act != B200OV_ACT_SIGMOID;
 }
 
+#ifdef B200OV_F16_TRACE
+extern "C" int b200ov_debug_f16_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, f16::g_f16_trace, sizeof(f16::g_f16_trace)) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 unsigned int* f16x2_status_word() {
   unsigned int* p = nullptr;
   if (cudaGetSymbolAddress(reinterpret_cast<void**>(&p), f16::g_status_word) != cudaSuccess) return nullptr;
@@ -617,14 +648,24 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
     my = mh;       // never dereferenced
   }
   unsigned int* status = f16x2_status_word();
-  if (p.wide_loads) {
-    if (block_n == 128) return f16::launch<128, 3, true>(p, x, bias, y, status, mh, ml, my, s);
-    if (block_n == 64) return f16::launch<64, 4, true>(p, x, bias, y, status, mh, ml, my, s);
-    return f16::launch<32, 4, true>(p, x, bias, y, status, mh, ml, my, s);
+  static int sb128 = -1;      // developer knob: B ring depth of the 128-wide tile (B200OV_F16_SB = 3..6)
+  if (sb128 < 0) {
+    const char* e = getenv("B200OV_F16_SB");
+    sb128 = e ? atoi(e) : 4;
+    if (sb128 < 3 || sb128 > 6) sb128 = 4;
   }
-  if (block_n == 128) return f16::launch<128, 3, false>(p, x, bias, y, status, mh, ml, my, s);
-  if (block_n == 64) return f16::launch<64, 4, false>(p, x, bias, y, status, mh, ml, my, s);
-  return f16::launch<32, 4, false>(p, x, bias, y, status, mh, ml, my, s);
+#define B200OV_F16_LAUNCH(N_, SB_) \
+  (p.wide_loads ? f16::launch<N_, SB_, true>(p, x, bias, y, status, mh, ml, my, s) \
+                : f16::launch<N_, SB_, false>(p, x, bias, y, status, mh, ml, my, s))
+  if (block_n == 128) {
+    if (sb128 == 3) return B200OV_F16_LAUNCH(128, 3);
+    if (sb128 == 5) return B200OV_F16_LAUNCH(128, 5);
+    if (sb128 == 6) return B200OV_F16_LAUNCH(128, 6);
+    return B200OV_F16_LAUNCH(128, 4);
+  }
+  if (block_n == 64) return B200OV_F16_LAUNCH(64, 6);
+  return B200OV_F16_LAUNCH(32, 6);
+#undef B200OV_F16_LAUNCH
 }
 
 }  // namespace b200ov
