@@ -51,7 +51,10 @@ constexpr int SLOT_K = 32;             // K elements per A slot (4 units of 8 ch
 constexpr int A_SLOTS = 4;             // TMEM ring depth
 constexpr int A_COL0 = 384;            // TMEM columns [384, 512): A ring, 32 columns per slot (16 hi + 16 lo)
 constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
-constexpr int CHUNK = 2;               // slots per promotion chunk (64 K elements)
+#ifndef B200OV_F16_CHUNK
+#define B200OV_F16_CHUNK 4
+#endif
+constexpr int CHUNK = B200OV_F16_CHUNK;               // slots per promotion chunk (128 K elements, 8 hi*hi MMAs)
 constexpr int NUM_SETS = 2;             // producer warp sets
 constexpr int SET_THREADS = 128;       // threads that build one A slot
 constexpr int NUM_EPILOGUE = 128;
@@ -260,7 +263,10 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           if ((slot & 1) == 0) F16_WAIT(2, bar_b_full(bs), (bcount / SB) & 1);
           const int as = acount % A_SLOTS;
           F16_WAIT(3, bar_a_full(as), (acount / A_SLOTS) & 1);
-          tc_fence_after();
+          F16_TIMED(4, tc_fence_after());
+#ifdef B200OV_F16_TRACE
+          const long long t_issue0_ = clock64();
+#endif
           if (elect_one_sync()) {
             const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
             const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
@@ -279,6 +285,9 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
             if (last) umma_commit(bar_cross_full);
           }
           __syncwarp();
+#ifdef B200OV_F16_TRACE
+          tr_[5] += clock64() - t_issue0_;
+#endif
           ++acount;
           if ((slot & 1) || last) ++bcount;
           if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
