@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 
 // NCHW -> NHWC for few channels (the network input: C = 1 or 3).  The tiled transpose above wastes most
 // of its 32-row tile here; instead a thread owns one pixel, reads its C planes (coalesced across the warp)
-// and writes the pixel's channel run.  PAD4: y_ld == 4 >= C, one 128-bit store per pixel with the unused
-// lanes zeroed (the tcgen05 stem convolution gathers 16-byte channel runs and needs finite padding).
-template <int MAXC, bool PAD4>
+// and writes the pixel's channel run.  PAD = 4 / 8: y_ld == PAD >= C, 128-bit stores with the unused lanes
+// zeroed (the tcgen05 stem convolution gathers whole 8-channel runs and needs finite padding).
+template <int MAXC, int PAD>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                   long long pixels, int c, int hw, int y_ld, int has_scale,
                                                                   const float* __restrict__ scale_vec, float scale_s,
@@ -75,8 +75,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* _
         if (has_shift) v[ch] = __fadd_rn(v[ch], sf[ch]);
       }
     }
-    if constexpr (PAD4) {
+    if constexpr (PAD == 4) {
       *reinterpret_cast<float4*>(y + pix * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (PAD == 8) {
+      *reinterpret_cast<float4*>(y + pix * 8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(y + pix * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
 #pragma unroll
       for (int ch = 0; ch < MAXC; ++ch)
@@ -136,11 +139,14 @@ int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, i
   if (c <= 4 && n > 0) {
     const long long pixels = (long long)n * hw;
     cudaStream_t s = as_stream(stream);
-    if (y_ld == 4 && aligned16(y))
-      nchw_to_nhwc_smallc_kernel<4, true><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+    if (y_ld == 8 && aligned16(y))
+      nchw_to_nhwc_smallc_kernel<4, 8><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                           scale_s, has_shift, shift_vec, shift_s);
+    else if (y_ld == 4 && aligned16(y))
+      nchw_to_nhwc_smallc_kernel<4, 4><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
                                                                               scale_s, has_shift, shift_vec, shift_s);
     else
-      nchw_to_nhwc_smallc_kernel<4, false><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+      nchw_to_nhwc_smallc_kernel<4, 0><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
                                                                                scale_s, has_shift, shift_vec, shift_s);
     B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
     return B200OV_OK;
