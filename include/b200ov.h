@@ -53,8 +53,9 @@ enum {
   B200OV_MATH_FP32 = 1,     /* CUDA-core FP32 FFMA implicit GEMM                                */
   B200OV_MATH_TF32X3 = 2,   /* tcgen05 kind::tf32, hi/lo split, 3 MMAs, FP32 accumulate in TMEM */
   B200OV_MATH_TF32 = 3,     /* tcgen05 kind::tf32 single pass (1e-3 tolerance class)            */
-  B200OV_MATH_F16X2 = 4     /* tcgen05 kind::f16, FP16 hi/lo split, 3 MMAs, A operand in TMEM;  *
+  B200OV_MATH_F16X2 = 4,    /* tcgen05 kind::f16, FP16 hi/lo split, 3 MMAs, A operand in TMEM;  *
                              * FP32-accurate for |values| < 65504, overflow raises the status word */
+  B200OV_MATH_SAFE = 5      /* AUTO without F16X2 (full FP32 exponent range): 3xTF32, else FFMA  */
 };
 
 /* ---- library / device -------------------------------------------------------------------- */
@@ -122,6 +123,9 @@ int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_p
  * repeats the inference with B200OV_MATH_TF32X3.  The reference has no such condition: its numpy kernels
  * compute in FP32 throughout (Convolution.py:83-84). */
 int b200ov_status_word(void** device_ptr);
+/* Clear the status word / copy it to (pinned) host memory, both asynchronously on `stream`. */
+int b200ov_status_reset(void* stream);
+int b200ov_status_fetch(uint32_t* host_out, void* stream);
 
 /* ---- depthwise GroupConvolution ------------------------------------------------------------ */
 typedef struct {

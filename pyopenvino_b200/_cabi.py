@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, 'libb200ov.so')
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_CLAMP, ACT_SIGMOID = 0, 1, 2, 3
-MATH_AUTO, MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_F16X2 = 0, 1, 2, 3, 4
+MATH_AUTO, MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_F16X2, MATH_SAFE = 0, 1, 2, 3, 4, 5
 POOL_MAX, POOL_AVG_REF = 0, 1
 
 
@@ -71,6 +71,8 @@ SIGNATURES = {
     'b200ov_conv2d': [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
     'b200ov_matmul': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P],
     'b200ov_status_word': [C.POINTER(C.c_void_p)],
+    'b200ov_status_reset': [_P],
+    'b200ov_status_fetch': [_P, _P],
     'b200ov_pack_dw_weights': [_P, _P, _I, _I, _I, _P],
     'b200ov_dwconv2d': [C.POINTER(DwConvDesc), _P, _P, _P, _P, _P],
     'b200ov_pool2d': [C.POINTER(PoolDesc), _P, _P, _P, _P, _P],

@@ -60,8 +60,10 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
       return conv2d_tcgen05(d, x, tf32_section(d, w_packed), bias, y, s, false);
     case B200OV_MATH_F16X2:
       return conv2d_f16x2(d, x, f16_section(d, w_packed), bias, y, s);
-    case B200OV_MATH_AUTO: {
+    case B200OV_MATH_AUTO:
       if (f16x2_eligible(d, x)) return conv2d_f16x2(d, x, f16_section(d, w_packed), bias, y, s);
+      /* fall through */
+    case B200OV_MATH_SAFE: {
       if (conv2d_tcgen05(d, x, nullptr, bias, y, s, true) == B200OV_OK) {
         b200ov_conv_desc dd = *d;
         dd.math = B200OV_MATH_TF32X3;
@@ -95,6 +97,21 @@ int b200ov_status_word(void** device_ptr) {
   unsigned int* p = f16x2_status_word();
   if (p == nullptr) return set_error(B200OV_ERR_CUDA, "status_word: cudaGetSymbolAddress failed");
   *device_ptr = p;
+  return B200OV_OK;
+}
+
+int b200ov_status_reset(void* stream) {
+  unsigned int* p = f16x2_status_word();
+  if (p == nullptr) return set_error(B200OV_ERR_CUDA, "status_reset: cudaGetSymbolAddress failed");
+  B200OV_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned int), as_stream(stream)));
+  return B200OV_OK;
+}
+
+int b200ov_status_fetch(uint32_t* host_out, void* stream) {
+  B200OV_REQUIRE(host_out, "status_fetch: null argument");
+  unsigned int* p = f16x2_status_word();
+  if (p == nullptr) return set_error(B200OV_ERR_CUDA, "status_fetch: cudaGetSymbolAddress failed");
+  B200OV_CUDA(cudaMemcpyAsync(host_out, p, sizeof(unsigned int), cudaMemcpyDeviceToHost, as_stream(stream)));
   return B200OV_OK;
 }
 

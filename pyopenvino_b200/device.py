@@ -41,6 +41,11 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def synchronize():
+    """Wait for everything queued on the launch stream."""
+    torch.cuda.current_stream().synchronize()
+
+
 class Arena:
     """Bump allocator over a few large torch buffers.  `reset()` rewinds it; an identical sequence of
     `alloc` calls then returns identical addresses, which is what lets one eager warm-up run size the

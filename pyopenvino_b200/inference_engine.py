@@ -541,13 +541,18 @@ class Executable_Network:
         if verbose:
             print('# node_id node_name time (sec)')
         stime = time.time()
+        from . import kernels
         with torch.cuda.stream(self.stream):
+            kernels.status_reset()
             if graph_mode:
                 res = self._infer_graph()
             else:
                 self.run_tasks(verbose)
+                kernels.status_fetch()
                 self.stream.synchronize()
                 res = {G.nodes[n]['name']: G.nodes[n]['result'] for n, _ in self.ienet.find_node_by_type('Result')}
+            if kernels.status_value() != 0:
+                res = self._infer_full_range(inputs, verbose)
         etime = time.time()
         if verbose:
             print('@TOTAL_TIME,', etime - stime)
@@ -652,10 +657,39 @@ class Executable_Network:
         from . import _cabi
         _cabi.call('b200ov_graph_launch', self._graph, C.c_void_p(self.stream.cuda_stream))
 
+    def _infer_full_range(self, inputs: dict, verbose: bool = False):
+        """The f16x2 contractions saw a non-finite output: an operand left the FP16 range (|v| > 65504) or the
+        data holds inf / NaN.  Repeat this inference eagerly with the FP32-range kernels (3xTF32 / FFMA), whose
+        results follow the reference for any finite FP32 input.  Rare by construction; counted in
+        `self.range_fallbacks`."""
+        from . import _cabi, kernels
+        from . import device as dev
+        G = self.ienet.G
+        self.range_fallbacks = getattr(self, 'range_fallbacks', 0) + 1
+        saved_params = {}
+        for node_name, val in inputs.items():
+            for node in G.nodes:
+                if G.nodes[node]['name'] == node_name:
+                    saved_params[node] = G.nodes[node].get('param')
+                    G.nodes[node]['param'] = val
+        saved_math = kernels.default_math
+        kernels.default_math = _cabi.MATH_SAFE
+        dev.set_arena(None)
+        try:
+            self._run(verbose=verbose, capture=False)
+            self.stream.synchronize()
+        finally:
+            kernels.default_math = saved_math
+            for node, val in saved_params.items():
+                G.nodes[node]['param'] = val
+        return {G.nodes[n]['name']: G.nodes[n]['result'] for n, _ in self.ienet.find_node_by_type('Result')}
+
     def fetch_outputs(self):
+        from . import kernels
         res = {}
         for name, arr in self._static_out.items():
             self._out_host[name][:arr.size].copy_(arr.t[:arr.size], non_blocking=True)
+        kernels.status_fetch()
         self.stream.synchronize()
         for name, arr in self._static_out.items():
             res[name] = self._out_host[name][:arr.size].numpy().reshape(arr.shape).copy()

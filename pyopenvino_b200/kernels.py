@@ -39,6 +39,27 @@ def _s():
     return C.c_void_p(dev.stream())
 
 
+# ---- range status of the f16x2 contractions -----------------------------------------------------
+_status_host = None
+
+
+def status_reset():
+    """Clear the library's sticky status word on the current stream (start of an inference)."""
+    _cabi.call('b200ov_status_reset', _s())
+
+
+def status_fetch():
+    """Queue a D2H copy of the status word into pinned memory; read `status_value()` after a stream sync."""
+    global _status_host
+    if _status_host is None:
+        _status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    _cabi.call('b200ov_status_fetch', C.c_void_p(_status_host.data_ptr()), _s())
+
+
+def status_value():
+    return 0 if _status_host is None else int(_status_host[0])
+
+
 # ---- host <-> device ------------------------------------------------------------------------
 
 def upload(arr, keep_host=False):

@@ -33,6 +33,5 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
     kn, kc, kh, kw = w.shape
     out_hw = common_def.spatial_output_shape((h, wd), (kh, kw), strides, pads_begin, pads_end, 'floor', auto_pad, True)
     f = fused or {}
-    y = kernels.conv2d(x, w, strides, pads_begin, out_hw, bias=f.get('bias'), act=f.get('act'), out=f.get('out'),
-                       math=plugin_util.math_mode(kernel_type))
-    return plugin_util.finish(node, inputs, y)
+    return plugin_util.run_contraction(node, inputs, kernel_type, lambda math: kernels.conv2d(
+        x, w, strides, pads_begin, out_hw, bias=f.get('bias'), act=f.get('act'), out=f.get('out'), math=math))

@@ -17,7 +17,6 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
     common_def.validate_inputs(node, inputs)
     data = node['data']
     f = fused or {}
-    y = kernels.matmul(inputs[0], inputs[1], transpose_a=(data['transpose_a'] == 'true'),
-                       transpose_b=(data['transpose_b'] == 'true'), bias=f.get('bias'), act=f.get('act'),
-                       math=plugin_util.math_mode(kernel_type))
-    return plugin_util.finish(node, inputs, y)
+    return plugin_util.run_contraction(node, inputs, kernel_type, lambda math: kernels.matmul(
+        inputs[0], inputs[1], transpose_a=(data['transpose_a'] == 'true'), transpose_b=(data['transpose_b'] == 'true'),
+        bias=f.get('bias'), act=f.get('act'), math=math))

@@ -15,7 +15,7 @@ dtype / shape validation first.  Extensions, all optional and ignored by referen
 from . import _cabi, common_def
 from .device import is_device
 
-_MATH = {'fp32': _cabi.MATH_FP32, 'tf32x3': _cabi.MATH_TF32X3, 'tf32': _cabi.MATH_TF32, 'f16x2': _cabi.MATH_F16X2}
+_MATH = {'fp32': _cabi.MATH_FP32, 'tf32x3': _cabi.MATH_TF32X3, 'tf32': _cabi.MATH_TF32, 'f16x2': _cabi.MATH_F16X2, 'safe': _cabi.MATH_SAFE}
 
 
 def math_mode(kernel_type):
@@ -31,6 +31,23 @@ def finish(node, inputs, result):
     if host_in_host_out(inputs) and is_device(result):
         result = result.numpy()
     return {port: result}
+
+
+def run_contraction(node, inputs, kernel_type, run):
+    """Convolution / MatMul: `run(math)` launches the kernel.  In host-in / host-out mode with the default
+    arithmetic the f16x2 range flag is checked here (the executor checks it once per inference instead):
+    a non-finite output repeats the node with the FP32-range kernels."""
+    math = math_mode(kernel_type)
+    if not (host_in_host_out(inputs) and math is None):
+        return finish(node, inputs, run(math))
+    from . import device as dev, kernels
+    kernels.status_reset()
+    y = run(None)
+    kernels.status_fetch()
+    dev.synchronize()
+    if kernels.status_value() != 0:
+        y = run(_cabi.MATH_SAFE)
+    return finish(node, inputs, y)
 
 
 def require_fp32_output(node):

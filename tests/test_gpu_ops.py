@@ -208,3 +208,22 @@ def test_contract_violation_raises(plugins):
     with pytest.raises(AssertionError):
         node['input'][0]['dims'] = (1, 3, 8, 8)
         plugins['ReLU'].compute(node, {0: x.astype(np.float64)})
+
+
+def test_f16x2_range_overflow_falls_back_to_full_range(plugins):
+    """An activation beyond the FP16 range (65504) makes the f16x2 contraction raise the status word; the
+    plugin (host-in / host-out) then repeats the node with the FP32-range kernels, so the result still
+    matches the reference.  With kernel_type='f16x2' pinned, the overflow is visible as a non-finite output."""
+    from oracle import ref_ops
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((1, 16, 9, 9)).astype(np.float32)
+    x[0, 3, 4, 4] = 3.0e5
+    w = (rng.standard_normal((24, 16, 3, 3)) * 0.1).astype(np.float32)
+    node = _conv_node(x, w, 1, (1, 1), (1, 1))
+    want = ref_ops.conv_special(x, w, (1, 1), (1, 1), (1, 1), 'explicit')
+    got = plugins['Convolution'].compute(node, {0: x, 1: w}, kernel_type='numpy')[2]
+    assert np.all(np.isfinite(got))
+    ok, msg = close(got, want, rtol=1e-4, atol=1e-5 * 3.0e5)       # absolute slack scaled to the 3e5 activation
+    assert ok, msg
+    pinned = plugins['Convolution'].compute(node, {0: x, 1: w}, kernel_type='f16x2')[2]
+    assert not np.all(np.isfinite(pinned))
