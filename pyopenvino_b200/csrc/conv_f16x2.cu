@@ -72,6 +72,8 @@ struct Params {
   float lo, hi;
   int tma_store;                       // 1: output written by TMA (y 16-byte aligned, y_ld % 4 == 0)
   int wide_loads;                      // 1: 256-bit gathers (x 32-byte aligned, x_ld % 8 == 0)
+  int pair4;                           // 1: cin <= 4 with a pixel pitch of 4 floats: a unit is two horizontally
+                                       //    adjacent filter taps x 4 channels (d_upt then divides by units per filter ROW)
   FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots;
 };
 
@@ -172,7 +174,7 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
   return r;
 }
 
-template <int BLOCK_N, int SB, bool WIDE>
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
@@ -330,15 +332,34 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         }
       }
       const uint32_t unit = slot * 4 + u4;
-      uint32_t tap, cu, ky, kx;
-      p.d_upt.divmod(unit, tap, cu);
-      p.d_kw.divmod(tap, ky, kx);
       const bool uvalid = unit < (uint32_t)p.units;
-      const int off = ((int)ky * p.w + (int)kx) * p.x_ld + (int)cu * 8;
+      if constexpr (!PAIR) {
+        uint32_t tap, cu, ky, kx;
+        p.d_upt.divmod(unit, tap, cu);
+        p.d_kw.divmod(tap, ky, kx);
+        const int off = ((int)ky * p.w + (int)kx) * p.x_ld + (int)cu * 8;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
-        dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, WIDE);
+        for (int r = 0; r < 4; ++r) {
+          const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
+          dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, WIDE);
+        }
+      } else {
+        // two adjacent taps (ky, 2*kxp) and (ky, 2*kxp + 1): with a pixel pitch of 4 floats they are 8 contiguous
+        // floats, but each half has its own bounds test (the image edge can fall between them)
+        uint32_t ky, kxp;
+        p.d_upt.divmod(unit, ky, kxp);
+        const int kx = 2 * (int)kxp;
+        const int off = ((int)ky * p.w + kx) * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const bool row_ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h;
+          const bool ok0 = row_ok && (unsigned)(rix[r] + kx) < (unsigned)p.w;
+          const bool ok1 = row_ok && (unsigned)(rix[r] + kx + 1) < (unsigned)p.w;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ok0 ? rbase[r] + off : g_zero_run));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ok1 ? rbase[r] + off + 4 : g_zero_run));
+          dst[r].v[0] = a.x; dst[r].v[1] = a.y; dst[r].v[2] = a.z; dst[r].v[3] = a.w;
+          dst[r].v[4] = b.x; dst[r].v[5] = b.y; dst[r].v[6] = b.z; dst[r].v[7] = b.w;
+        }
       }
     };
     auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
@@ -498,7 +519,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
 // OIHW -> [plane hi | plane lo], each [coutp][kpad] halfs, K ordered (slot, kappa) with the in-slot permutation
 // the A producers use: kappa = 16*b + 4*u + j  <->  unit 4*slot + u, channel 4*b + j of that unit.
 __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int kh,
-                                        int kw, int coutp, int kpad, int upt, int units) {
+                                        int kw, int coutp, int kpad, int upt, int units, int pair4) {
   const long long plane = (long long)coutp * kpad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < plane;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -509,10 +530,15 @@ __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __r
     const int cj = ((kappa >> 4) << 2) + (kappa & 3);
     float v = 0.f;
     if (n < cout && unit < units) {
-      const int tap = unit / upt, c = (unit - tap * upt) * 8 + cj;
-      if (c < cin) {
-        const int ky = tap / kw, kx = tap - ky * kw;
-        v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+      if (pair4) {                       // unit = (filter row ky, tap pair kxp): taps 2*kxp, 2*kxp + 1, 4 channels each
+        const int ky = unit / upt, kx = 2 * (unit - ky * upt) + (cj >> 2), c = cj & 3;
+        if (kx < kw && c < cin) v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+      } else {
+        const int tap = unit / upt, c = (unit - tap * upt) * 8 + cj;
+        if (c < cin) {
+          const int ky = tap / kw, kx = tap - ky * kw;
+          v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+        }
       }
     }
     const __half h = __float2half_rn(v);
@@ -554,11 +580,11 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
   return B200OV_OK;
 }
 
-template <int BLOCK_N, int SB, bool WIDE>
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
 static int launch(const Params& p, const float* x, const float* bias, float* y, unsigned int* status, const CUtensorMap& mh,
                   const CUtensorMap& ml, const CUtensorMap& my, cudaStream_t s) {
   using L = Smem<BLOCK_N, SB>;
-  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR>;
   static bool configured = false;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -574,9 +600,12 @@ __device__ unsigned int g_status_word;     // sticky: bit 0 = a non-finite value
 
 }  // namespace f16
 
+// cin <= 4: "pair" layout (a unit = two adjacent taps of one filter row x 4 channels; upt = units per filter row);
+// otherwise a unit = 8 channels of one tap (upt = units per tap).
 void f16_weight_dims(int cout, int cin, int kh, int kw, int* coutp, int* kpad, int* upt, int* units) {
-  const int u = ceil_div(cin, 8);
-  const int n_units = kh * kw * u;
+  const bool pair4 = cin <= 4;
+  const int u = pair4 ? ceil_div(kw, 2) : ceil_div(cin, 8);
+  const int n_units = pair4 ? kh * u : kh * kw * u;
   if (coutp) *coutp = round_up(cout, 8);
   if (kpad) *kpad = round_up(n_units, 8) * 8;         // whole B stages of 64 K-elements
   if (upt) *upt = u;
@@ -593,15 +622,17 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
   int coutp, kpad, upt, units;
   f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, &upt, &units);
   f16::pack_f16_weights_kernel<<<bw_grid((long long)coutp * kpad, 256), 256, 0, s>>>(w_oihw, reinterpret_cast<__half*>(out), cout,
-                                                                                    cin, kh, kw, coutp, kpad, upt, units);
+                                                                                    cin, kh, kw, coutp, kpad, upt, units,
+                                                                                    cin <= 4 ? 1 : 0);
   B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
   return B200OV_OK;
 }
 
-// The gather reads whole 8-channel runs: either cin is a multiple of 8, or the pixel pitch covers the padded
-// run (x_ld >= round_up(cin, 8); the producer of x zero-fills the pad lanes, e.g. the network-input layout kernel).
+// The gather reads 8-float runs: either cin is a multiple of 8 (a run = 8 channels of one tap), or cin <= 4 with a
+// pixel pitch of exactly 4 floats (a run = two adjacent taps; the producer of x zero-fills the pad lanes, e.g. the
+// network-input layout kernel writes a 3-channel image with pitch 4).
 bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
-  return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || d->x_ld >= round_up(d->cin, 8)) &&
+  return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || (d->cin <= 4 && d->x_ld == 4)) &&
          d->act != B200OV_ACT_SIGMOID;
 }
 
@@ -620,7 +651,7 @@ unsigned int* f16x2_status_word() {
 // `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.
 int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
   if (!f16x2_eligible(d, x))
-    return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with 8-channel runs (cin %% 8 == 0 or x_ld >= cin padded to 8) and no fused Sigmoid");
+    return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with cin %% 8 == 0 (or cin <= 4 at a pixel pitch of 4) and no fused Sigmoid");
   f16::Params p;
   memset(&p, 0, sizeof(p));
   p.h = d->h; p.w = d->w; p.cin = d->cin; p.cout = d->cout; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.pl = d->pl;
@@ -640,7 +671,8 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
   p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
   p.tma_store = (d->y_ld % 4 == 0) && aligned16(y);
-  p.wide_loads = (d->x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
+  p.pair4 = d->cin <= 4;
+  p.wide_loads = !p.pair4 && (d->x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(d->kw);
   p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
   const __half* hi_plane = reinterpret_cast<const __half*>(wt);
@@ -661,12 +693,14 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
   if (sb128 < 0) {
     const char* e = getenv("B200OV_F16_SB");
     sb128 = e ? atoi(e) : 4;
-    if (sb128 < 3 || sb128 > 6) sb128 = 4;
+    if (sb128 < 2 || sb128 > 6) sb128 = 4;
   }
 #define B200OV_F16_LAUNCH(N_, SB_) \
-  (p.wide_loads ? f16::launch<N_, SB_, true>(p, x, bias, y, status, mh, ml, my, s) \
-                : f16::launch<N_, SB_, false>(p, x, bias, y, status, mh, ml, my, s))
+  (p.pair4 ? f16::launch<N_, SB_, false, true>(p, x, bias, y, status, mh, ml, my, s) \
+           : p.wide_loads ? f16::launch<N_, SB_, true, false>(p, x, bias, y, status, mh, ml, my, s) \
+                          : f16::launch<N_, SB_, false, false>(p, x, bias, y, status, mh, ml, my, s))
   if (block_n == 128) {
+    if (sb128 == 2) return B200OV_F16_LAUNCH(128, 2);
     if (sb128 == 3) return B200OV_F16_LAUNCH(128, 3);
     if (sb128 == 5) return B200OV_F16_LAUNCH(128, 5);
     if (sb128 == 6) return B200OV_F16_LAUNCH(128, 6);

@@ -765,6 +765,9 @@ class Executable_Network:
                 for it in range(iters + 1):
                     arena.reset()
                     self._step_events = []
+                    # keep the GPU busy while the host queues the whole pass, so the events around each step
+                    # measure kernel time and not the host's launch gaps
+                    torch.cuda._sleep(40000000)
                     self._run(capture=self.use_graph)
                     self.stream.synchronize()
                     if it > 0:

@@ -94,9 +94,9 @@ def to_nhwc(x, scale=None, shift=None, out=None):
     assert x.layout == 'plain' and x.ndim == 4
     n, c, h, w = x.shape
     if out is None:
-        # a 3-channel network input gets a pixel pitch of 8 floats (zero-filled pad lanes) so the stem
-        # convolution can gather whole 8-channel runs and run on the tensor cores (conv_f16x2.cu)
-        ld = 8 if c == 3 else c
+        # a 3-channel network input gets a pixel pitch of 4 floats (zero-filled pad lane) so the stem
+        # convolution can gather 16-byte runs and run on the tensor cores (conv_f16x2.cu, "pair" mode)
+        ld = 4 if c == 3 else c
         out = DeviceArray(dev.alloc_f32(n * h * w * ld), x.shape, 'nhwc', ld=ld)
     sv, ss, hs = _affine_operand(scale, c)
     bv, bs, hb = _affine_operand(shift, c)
