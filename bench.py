@@ -166,7 +166,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='images per GPU per step')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for cpu_baseline')
     ap.add_argument('--layers-out', default=None, help='write the per-layer roofline table (JSON) here')
-    ap.add_argument('--math', default=None, choices=[None, 'fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--math', default=None, choices=[None, 'fp32', 'tf32x3', 'tf32', 'f16x2', 'safe'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     model, default_batch, desc = WORKLOADS[args.workload]
@@ -276,21 +276,45 @@ def main():
                            'tflops': w['flops'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0.0,
                            'gbs': w['bytes'] / (s['ms'] * 1e-3) / 1e9 if s['ms'] > 0 else 0.0, 'roofline_ms': roof,
                            'frac_of_roofline': roof / s['ms'] if s['ms'] > 0 else 0.0})
-        top_kind = max(fam, key=lambda k: fam[k]['ms'])
-        top = fam[top_kind]
+        # families -> the CUDA kernel that runs them; the roofline object describes the dominant KERNEL
+        def kernel_of(kind):
+            if kind.startswith('conv') or kind == 'matmul':
+                return 'conv_f16x2_kernel'
+            return {'depthwise': 'dwconv3x3_strip_kernel', 'maxpool': 'pool_max_strip_kernel', 'lrn': 'lrn_vec4_kernel',
+                    'input_layout': 'nchw_to_nhwc_smallc_kernel'}.get(kind, kind)
+        kern = {}
+        for kind, f in fam.items():
+            k = kern.setdefault(kernel_of(kind), {'ms': 0.0, 'flops': 0, 'bytes': 0, 'launches': 0, 'families': []})
+            for key in ('ms', 'flops', 'bytes', 'launches'):
+                k[key] += f[key]
+            k['families'].append(kind)
+        top_kind = max(kern, key=lambda k: kern[k]['ms'])
+        top = kern[top_kind]
         ai = top['flops'] / max(top['bytes'], 1)
-        tensor_bound = ai > tf32x3_peak * 1e12 / (peaks['hbm_gbs'] * 1e9)
+        # the f16x2 contraction spends 3 tensor-core MMAs per FP32 product: its ridge point uses peak / 3
+        mma_per_product = 3 if top_kind == 'conv_f16x2_kernel' else 1
+        tensor_bound = ai > (tf32x3_peak / mma_per_product) * 1e12 / (peaks['hbm_gbs'] * 1e9)
         if tensor_bound:
             achieved = top['flops'] / (top['ms'] * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32x3_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32x3_peak}
+            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32x3_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32x3_peak,
+                    'mma_per_fp32_product': mma_per_product, 'tensor_pipe_frac': achieved * mma_per_product / tf32x3_peak}
         else:
             achieved = top['bytes'] / (top['ms'] * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs']}
-        roof.update({'traffic': None, 'kernel': top_kind, 'launches_per_step': top['launches'],
+        traffic = None
+        tpath = os.path.join(REPO, 'profiles', 'ncu_traffic.json')      # dram bytes per launch from an ncu capture of this command
+        if os.path.isfile(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(model, {}).get(top_kind)
+            except Exception:
+                traffic = None
+        roof.update({'traffic': traffic, 'kernel': top_kind, 'families': sorted(top['families']), 'launches_per_step': top['launches'],
                      'share_of_step': top['ms'] / total_ms if total_ms else None,
                      'algorithmic_gflop_per_step': top['flops'] / 1e9, 'algorithmic_mbytes_per_step': top['bytes'] / 1e6,
+                     'algorithmic_mbytes_per_launch': top['bytes'] / 1e6 / max(top['launches'], 1),
                      'avg_launch_ms': top['ms'] / max(top['launches'], 1), 'peak_source': peaks['source'],
-                     'peak_note': 'tensor peak = measured dense bf16 (sustained); FP32-accurate paths (FFMA, 3xTF32) cannot exceed ~1/6 of it'})
+                     'peak_note': 'tensor peak = measured dense bf16 (sustained); an FP32-accurate product costs 3 kind::f16 MMAs '
+                                  '(f16x2 split), so tensor_pipe_frac = 3 * achieved / peak is the share of the tensor pipe in use'})
         model_roof_ms = sum(l['roofline_ms'] for l in layers)
         line['roofline'] = roof
         line['model_roofline'] = {'sum_layer_roofline_ms': model_roof_ms, 'frac': model_roof_ms / (ms_total / args.steps),
