@@ -18,6 +18,9 @@
 //                          stage, 128B swizzle) into a shared-memory ring.
 //   warp 1      MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
 //                          shared memory; tcgen05.commit releases A slots / B stages / accumulators.
+//   warp 2      gate     : waits on every mbarrier a slot depends on, ahead of the MMA warp, and publishes a
+//                          "slots ready" counter (the MMA issue blocks on the tensor-pipe queue, so its own
+//                          waits must be short).
 //   warps 4-11  A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
 //                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split with packed
 //                          FP32 math, and tcgen05.st into a 4-slot TMEM ring.  Two sets of four warps work on
@@ -106,6 +109,7 @@ struct Smem {
   // b_full[SB], b_empty[SB], a_full[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full, cross_empty
   static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 6;
   static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
+  static constexpr int READY = TMEM_PTR + 8;                           // gate warp -> MMA warp: slots whose inputs are ready
   static constexpr int TOTAL = TMEM_PTR + 16 + 1024;                   // + slack for the 1024-byte alignment of the base
 };
 
@@ -211,6 +215,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     }
     mbar_init(bar_cross_full, 1);
     mbar_init(bar_cross_empty, NUM_EPILOGUE);
+    *reinterpret_cast<volatile uint32_t*>(base_ptr + L::READY) = 0u;
     fence_mbar_init();
     prefetch_tensormap(&map_hi);
     prefetch_tensormap(&map_lo);
@@ -226,7 +231,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
   const int num_stages = (p.num_slots + 1) >> 1;      // B stages per tile
 
   if (warp < 4) {
-    // warpgroup 0: B loader (warp 0), MMA issuer (warp 1), two idle warps.  Hand the registers to the others.
+    // warpgroup 0: B loader (warp 0), MMA issuer (warp 1), gate (warp 2), one idle warp.  Hand the registers to the others.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
     if (warp == 0) {
       // ================= B loader ====================================================================
@@ -259,12 +264,11 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         for (int slot = 0; slot < p.num_slots; ++slot) {
           const bool last = slot == p.num_slots - 1;
           const int buf = chunkcount & 1;
-          if (slot % CHUNK == 0) F16_WAIT(0, bar_main_empty(buf), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
-          if (slot == 0) F16_WAIT(1, bar_cross_empty, (tl & 1) ^ 1);                              // previous tile's cross terms read
           const int bs = bcount % SB;
-          if ((slot & 1) == 0) F16_WAIT(2, bar_b_full(bs), (bcount / SB) & 1);
           const int as = acount % A_SLOTS;
-          F16_WAIT(3, bar_a_full(as), (acount / A_SLOTS) & 1);
+          // all inputs of this slot (accumulators drained, B stage landed, A slot written) were awaited by the
+          // gate warp; a shared-memory counter costs one ~30-cycle load here instead of four mbarrier try_waits
+          F16_TIMED(3, wait_ready(base + L::READY, acount + 1));
           F16_TIMED(4, tc_fence_after());
 #ifdef B200OV_F16_TRACE
           const long long t_issue0_ = clock64();
@@ -296,6 +300,25 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         }
       }
       F16_TRACE_STORE(1, lane == 0);
+    } else if (warp == 2) {
+      // ================= gate ========================================================================
+      // Runs the MMA warp's waits ahead of it: the UTCHMMA issue blocks while the tensor-pipe queue is full,
+      // and four serial mbarrier waits per slot in the issuing thread left the pipe idle half of the time.
+      uint32_t acount = 0, bcount = 0, chunkcount = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int slot = 0; slot < p.num_slots; ++slot) {
+          const bool last = slot == p.num_slots - 1;
+          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(chunkcount & 1), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+          if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                                    // previous tile's cross terms read
+          if ((slot & 1) == 0) mbar_wait(bar_b_full(bcount % SB), (bcount / SB) & 1);
+          mbar_wait(bar_a_full(acount % A_SLOTS), (acount / A_SLOTS) & 1);
+          ++acount;
+          if ((slot & 1) || last) ++bcount;
+          if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
+          if (lane == 0) st_release_shared(base + L::READY, acount);
+          __syncwarp();
+        }
+      }
     }
   } else if (warp < 4 + 4 * NUM_SETS) {
     // ================= A producers: gather -> split -> TMEM ==========================================

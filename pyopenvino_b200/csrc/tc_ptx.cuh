@@ -68,6 +68,23 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// spin until the counter at `addr` reaches `target` (bounded like mbar_wait)
+__device__ __forceinline__ void wait_ready(uint32_t addr, uint32_t target) {
+  long long t0 = 0;
+  while ((int)(ld_acquire_shared(addr) - target) < 0) {
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
