@@ -51,13 +51,20 @@ using namespace ptx;
 
 constexpr int BLOCK_M = 128;
 constexpr int SLOT_K = 32;             // K elements per A slot (4 units of 8 channels)
-constexpr int A_SLOTS = 4;             // TMEM ring depth
-constexpr int A_COL0 = 384;            // TMEM columns [384, 512): A ring, 32 columns per slot (16 hi + 16 lo)
+// TMEM columns: [0, NBUF*N) hi*hi accumulator(s), [NBUF*N, (NBUF+1)*N) cross terms, then the A ring, 32 columns per
+// slot (16 hi + 16 lo), at most 8 slots.
+#ifndef B200OV_F16_NBUF128
+#define B200OV_F16_NBUF128 2
+#endif
+constexpr int nbuf(int block_n) { return block_n > 64 ? B200OV_F16_NBUF128 : 2; }
+constexpr int a_col0(int block_n) { return (nbuf(block_n) + 1) * block_n; }
+constexpr int a_slots(int block_n) { return (512 - a_col0(block_n)) / 32 < 8 ? (512 - a_col0(block_n)) / 32 : 8; }
 constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
 #ifndef B200OV_F16_CHUNK
 #define B200OV_F16_CHUNK 4
 #endif
-constexpr int CHUNK = B200OV_F16_CHUNK;               // slots per promotion chunk (128 K elements, 8 hi*hi MMAs)
+constexpr int CHUNK2 = B200OV_F16_CHUNK;              // slots per promotion chunk (128 K elements, 8 hi*hi MMAs)
+constexpr int chunk_slots(int block_n) { return nbuf(block_n) == 1 ? 8 : CHUNK2; }
 constexpr int NUM_SETS = 2;             // producer warp sets
 constexpr int SET_THREADS = 128;       // threads that build one A slot
 constexpr int NUM_EPILOGUE = 128;
@@ -107,6 +114,7 @@ struct Smem {
   static constexpr int BIAS = STAGING + STAGING_BYTES;                 // BLOCK_N floats
   static constexpr int BARS = BIAS + BLOCK_N * 4;
   // b_full[SB], b_empty[SB], a_full[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full, cross_empty
+  static constexpr int A_SLOTS = a_slots(BLOCK_N);
   static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 6;
   static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
   static constexpr int READY = TMEM_PTR + 8;                           // gate warp -> MMA warp: slots whose inputs are ready
@@ -184,6 +192,10 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y) {
   using L = Smem<BLOCK_N, SB>;
+  constexpr int A_SLOTS = a_slots(BLOCK_N);
+  constexpr int A_COL0 = a_col0(BLOCK_N);
+  constexpr int NBUF = nbuf(BLOCK_N);
+  constexpr int CHUNK = chunk_slots(BLOCK_N);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -257,13 +269,13 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     } else if (warp == 1) {
       // ================= MMA issuer ==================================================================
       constexpr uint32_t idesc = instr_desc(BLOCK_N);
-      const uint32_t tmem_cross = tmem_base + 2 * BLOCK_N;
+      const uint32_t tmem_cross = tmem_base + NBUF * BLOCK_N;
       uint32_t acount = 0, bcount = 0, chunkcount = 0;
       F16_TRACE_DECL
       for (int tl = 0; tl < my_tiles; ++tl) {
         for (int slot = 0; slot < p.num_slots; ++slot) {
           const bool last = slot == p.num_slots - 1;
-          const int buf = chunkcount & 1;
+          const int buf = chunkcount % NBUF;
           const int bs = bcount % SB;
           const int as = acount % A_SLOTS;
           // all inputs of this slot (accumulators drained, B stage landed, A slot written) were awaited by the
@@ -308,7 +320,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       for (int tl = 0; tl < my_tiles; ++tl) {
         for (int slot = 0; slot < p.num_slots; ++slot) {
           const bool last = slot == p.num_slots - 1;
-          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(chunkcount & 1), ((chunkcount >> 1) & 1) ^ 1);   // promotion of chunk-2 done
+          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(chunkcount % NBUF), ((chunkcount / NBUF) & 1) ^ 1);   // promotion of chunk-NBUF done
           if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                                    // previous tile's cross terms read
           if ((slot & 1) == 0) mbar_wait(bar_b_full(bcount % SB), (bcount / SB) & 1);
           mbar_wait(bar_a_full(acount % A_SLOTS), (acount / A_SLOTS) & 1);
@@ -448,8 +460,8 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       }
       const int num_chunks = (p.num_slots + CHUNK - 1) / CHUNK;
       auto promote = [&]() {
-        const int buf = chunkcount & 1;
-        F16_WAIT(0, bar_main_full(buf), (chunkcount >> 1) & 1);
+        const int buf = chunkcount % NBUF;
+        F16_WAIT(0, bar_main_full(buf), (chunkcount / NBUF) & 1);
         tc_fence_after();
 #pragma unroll
         for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
@@ -471,7 +483,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
 #pragma unroll
       for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_lane + 2 * BLOCK_N + qb * 32, v);
+        tmem_ld_32x32b_x32(tmem_lane + NBUF * BLOCK_N + qb * 32, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[qb * 16 + j] = fma2(pack_u32x2(v[2 * j], v[2 * j + 1]), unscale, acc[qb * 16 + j]);
       }
