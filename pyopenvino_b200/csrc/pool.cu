@@ -38,86 +38,96 @@ __device__ __forceinline__ void storev(float* p, const float (&v)[V]) {
 }
 
 struct PoolStripP {
-  int h, w, sw, pt, pl, hp, wpad, oh, ow, x_ld, y_ld, th;
-  uint32_t total;                // work items = n * strips * ow * cg
-  FastDiv d_cg, d_ow, d_strips;
+  int h, w, pt, pl, hp, wpad, oh, ow, x_ld, y_ld, th;
+  uint32_t total;                // work items = n * strips * ceil(ow / TW) * cg
+  FastDiv d_cg, d_owt, d_strips;
 };
 
-// MaxPool, window KH x KW, row stride SH (column stride runtime), V = 4 channels per thread.
-template <int KH, int KW, int SH>
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// MaxPool, window KH x KW, stride S in both directions, 4 channels x TW adjacent output columns per thread.
+// Per input row a thread loads the (TW-1)*S + KW columns its TW windows cover once (1.5 loads per output for a
+// 3x3 stride-1 pool with TW = 4 instead of 3) and keeps the per-row maxima two vertically adjacent windows share.
+template <int KH, int KW, int S, int TW>
 __global__ void __launch_bounds__(256) pool_max_strip_kernel(PoolStripP p, const float* __restrict__ x,
                                                              const float* __restrict__ scale,
                                                              const float* __restrict__ shift, float* __restrict__ y) {
+  constexpr int NCOL = (TW - 1) * S + KW;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += stride) {
-    uint32_t q, g, q2, ox, img, strip;
+    uint32_t q, g, q2, oxt, img, strip;
     p.d_cg.divmod(idx, q, g);
-    p.d_ow.divmod(q, q2, ox);
+    p.d_owt.divmod(q, q2, oxt);
     p.d_strips.divmod(q2, img, strip);
     const int c0 = (int)g * 4;
+    const int ox0 = (int)oxt * TW;
     const int oy0 = (int)strip * p.th;
     const int oy1 = min(p.oh, oy0 + p.th);
     const float* ximg = x + (size_t)img * p.h * p.w * p.x_ld + c0;
-    float* yp = y + ((size_t)(img * p.oh + oy0) * p.ow + ox) * p.y_ld + c0;
-    const int px0 = (int)ox * p.sw;
+    float* yp = y + ((size_t)(img * p.oh + oy0) * p.ow + ox0) * p.y_ld + c0;
+    const int px0 = ox0 * S;
     const int ix0 = px0 - p.pl;
-    // column validity of the window (fixed for the strip): inside the padded tensor / inside the real tensor
-    bool col_in_pad[KW], col_in_x[KW];
+    // column state (fixed for the strip): inside the padded tensor / inside the real tensor / needed at all
+    bool col_in_pad[NCOL], col_in_x[NCOL];
 #pragma unroll
-    for (int kx = 0; kx < KW; ++kx) {
-      col_in_pad[kx] = px0 + kx < p.wpad;
-      col_in_x[kx] = ix0 + kx >= 0 && ix0 + kx < p.w;
+    for (int cidx = 0; cidx < NCOL; ++cidx) {
+      col_in_pad[cidx] = px0 + cidx < p.wpad;
+      const bool needed = ox0 + (cidx >= KW ? (cidx - KW) / S + 1 : 0) < p.ow;   // first output column that uses it exists
+      col_in_x[cidx] = needed && ix0 + cidx >= 0 && ix0 + cidx < p.w;
     }
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
     if (scale != nullptr) sc = __ldg(reinterpret_cast<const float4*>(scale + c0));
     if (shift != nullptr) sf = __ldg(reinterpret_cast<const float4*>(shift + c0));
-    // maximum over the window columns of padded row py; -inf when the row lies outside the padded tensor
-    auto row_max = [&](int py) -> float4 {
-      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (py >= p.hp) return m;
+    // per output column: maximum over its window columns of padded row py; -inf when the row lies outside the padded tensor
+    auto row_max = [&](int py, float4 (&m)[TW]) {
+#pragma unroll
+      for (int t = 0; t < TW; ++t) m[t] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (py >= p.hp) return;
       const int iy = py - p.pt;
       const bool row_in = iy >= 0 && iy < p.h;
       const float* xr = ximg + ((long long)(row_in ? iy : 0) * p.w + ix0) * p.x_ld;
-      float4 v[KW];
+      float4 v[NCOL];
 #pragma unroll
-      for (int kx = 0; kx < KW; ++kx) {
-        v[kx] = make_float4(0.f, 0.f, 0.f, 0.f);                       // the zero padding participates
-        if (row_in && col_in_x[kx]) v[kx] = __ldg(reinterpret_cast<const float4*>(xr + kx * p.x_ld));
+      for (int cidx = 0; cidx < NCOL; ++cidx) {
+        v[cidx] = make_float4(0.f, 0.f, 0.f, 0.f);                     // the zero padding participates
+        if (row_in && col_in_x[cidx]) v[cidx] = __ldg(reinterpret_cast<const float4*>(xr + cidx * p.x_ld));
       }
 #pragma unroll
-      for (int kx = 0; kx < KW; ++kx)
-        if (col_in_pad[kx]) {
-          m.x = fmaxf(m.x, v[kx].x); m.y = fmaxf(m.y, v[kx].y); m.z = fmaxf(m.z, v[kx].z); m.w = fmaxf(m.w, v[kx].w);
-        }
-      return m;
-    };
-    // Two output rows per iteration: their 2*SH new input rows are all requested before the first max is
-    // taken, so each thread keeps 2*SH*KW 128-bit loads in flight (the kernel is latency-, not LSU-bound).
-    constexpr int KEEP = KH > SH ? KH - SH : 0;      // rows shared by vertically adjacent windows
-    constexpr int NR = KH + SH;                      // padded rows under two vertically adjacent windows
-    float4 rm[NR];
+      for (int t = 0; t < TW; ++t)
 #pragma unroll
-    for (int r = 0; r < KEEP; ++r) rm[r] = row_max(oy0 * SH + r);
+        for (int kx = 0; kx < KW; ++kx)
+          if (col_in_pad[t * S + kx]) m[t] = max4(m[t], v[t * S + kx]);
+    };
+    // Two output rows per iteration: their 2*S new input rows are all requested before the first max is taken.
+    constexpr int KEEP = KH > S ? KH - S : 0;        // rows shared by vertically adjacent windows
+    constexpr int NR = KH + S;                       // padded rows under two vertically adjacent windows
+    float4 rm[NR][TW];
+#pragma unroll
+    for (int r = 0; r < KEEP; ++r) row_max(oy0 * S + r, rm[r]);
     for (int oy = oy0; oy < oy1; oy += 2) {
       const bool two = oy + 1 < oy1;
 #pragma unroll
-      for (int r = KEEP; r < NR; ++r) rm[r] = row_max((two || r < KH) ? oy * SH + r : p.hp);
+      for (int r = KEEP; r < NR; ++r) row_max((two || r < KH) ? oy * S + r : p.hp, rm[r]);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1 && !two) break;
-        float4 o = rm[t * SH];
+      for (int v2 = 0; v2 < 2; ++v2) {
+        if (v2 == 1 && !two) break;
 #pragma unroll
-        for (int r = 1; r < KH; ++r) {
-          const float4 m = rm[t * SH + r];
-          o.x = fmaxf(o.x, m.x); o.y = fmaxf(o.y, m.y); o.z = fmaxf(o.z, m.z); o.w = fmaxf(o.w, m.w);
+        for (int t = 0; t < TW; ++t) {
+          float4 o = rm[v2 * S][t];
+#pragma unroll
+          for (int r = 1; r < KH; ++r) o = max4(o, rm[v2 * S + r][t]);
+          if (scale != nullptr) { o.x = __fmul_rn(o.x, sc.x); o.y = __fmul_rn(o.y, sc.y); o.z = __fmul_rn(o.z, sc.z); o.w = __fmul_rn(o.w, sc.w); }
+          if (shift != nullptr) { o.x = __fadd_rn(o.x, sf.x); o.y = __fadd_rn(o.y, sf.y); o.z = __fadd_rn(o.z, sf.z); o.w = __fadd_rn(o.w, sf.w); }
+          if (ox0 + t < p.ow) *reinterpret_cast<float4*>(yp + t * p.y_ld) = o;
         }
-        if (scale != nullptr) { o.x = __fmul_rn(o.x, sc.x); o.y = __fmul_rn(o.y, sc.y); o.z = __fmul_rn(o.z, sc.z); o.w = __fmul_rn(o.w, sc.w); }
-        if (shift != nullptr) { o.x = __fadd_rn(o.x, sf.x); o.y = __fadd_rn(o.y, sf.y); o.z = __fadd_rn(o.z, sf.z); o.w = __fadd_rn(o.w, sf.w); }
-        *reinterpret_cast<float4*>(yp) = o;
         yp += (size_t)p.ow * p.y_ld;
       }
 #pragma unroll
-      for (int r = 0; r < KEEP; ++r) rm[r] = rm[r + 2 * SH];
+      for (int r = 0; r < KEEP; ++r)
+#pragma unroll
+        for (int t = 0; t < TW; ++t) rm[r][t] = rm[r + 2 * S][t];
     }
   }
 }
@@ -213,22 +223,23 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   if (d->n == 0) return B200OV_OK;
   const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned16(x) && aligned16(y) &&
                    (scale == nullptr || aligned16(scale)) && (shift == nullptr || aligned16(shift));
-  if (vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && (d->sh == 1 || d->sh == 2)) {
+  if (vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) {
     PoolStripP q;
-    q.h = d->h; q.w = d->w; q.sw = d->sw; q.pt = d->pt; q.pl = d->pl; q.hp = d->h + d->pt + d->pb;
+    q.h = d->h; q.w = d->w; q.pt = d->pt; q.pl = d->pl; q.hp = d->h + d->pt + d->pb;
     q.wpad = d->w + d->pl + d->pr; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld; q.y_ld = d->y_ld;
     q.th = d->oh < 8 ? d->oh : 8;
-    const int strips = ceil_div(d->oh, q.th), cg = d->c / 4;
-    const long long items = (long long)d->n * strips * d->ow * cg;
+    const int tw = d->sh == 1 ? 4 : 2;
+    const int strips = ceil_div(d->oh, q.th), cg = d->c / 4, owt = ceil_div(d->ow, tw);
+    const long long items = (long long)d->n * strips * owt * cg;
     if (items < 0x7fffffffLL) {
       q.total = (uint32_t)items;
-      q.d_cg = FastDiv(cg); q.d_ow = FastDiv(d->ow); q.d_strips = FastDiv(strips);
+      q.d_cg = FastDiv(cg); q.d_owt = FastDiv(owt); q.d_strips = FastDiv(strips);
       const int g = bw_grid(items, 256);
       cudaStream_t s = as_stream(stream);
-      if (d->kh == 3 && d->sh == 1) pool_max_strip_kernel<3, 3, 1><<<g, 256, 0, s>>>(q, x, scale, shift, y);
-      else if (d->kh == 3) pool_max_strip_kernel<3, 3, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
-      else if (d->sh == 1) pool_max_strip_kernel<2, 2, 1><<<g, 256, 0, s>>>(q, x, scale, shift, y);
-      else pool_max_strip_kernel<2, 2, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      if (d->kh == 3 && d->sh == 1) pool_max_strip_kernel<3, 3, 1, 4><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else if (d->kh == 3) pool_max_strip_kernel<3, 3, 2, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else if (d->sh == 1) pool_max_strip_kernel<2, 2, 1, 4><<<g, 256, 0, s>>>(q, x, scale, shift, y);
+      else pool_max_strip_kernel<2, 2, 2, 2><<<g, 256, 0, s>>>(q, x, scale, shift, y);
       B200OV_LAUNCH_CHECK("pool_max_strip_kernel");
       return B200OV_OK;
     }
