@@ -102,13 +102,24 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_strip_kernel(DwStripP p, con
     }
     const ulonglong2* zeros = reinterpret_cast<const ulonglong2*>(g_dw_zeros);
     ulonglong2 R[NB][NC];
+    // interior strips (no padded tap, both output columns exist) skip every bounds test and pointer select
+    const int iy_first = oy0 * S - p.pt, iy_last = (oy1 - 1) * S - p.pt + 2;
+    const bool interior = second && iy_first >= 0 && iy_last < p.h && ix0 >= 0 && ix0 + NC <= p.w;
+    const float* xcol0 = ximg + (long long)ix0 * p.x_ld;          // only dereferenced for valid taps
+    const int row_pitch = p.w * p.x_ld;
     auto load_row = [&](int iy, ulonglong2 (&dst)[NC]) {
-      const bool row_ok = iy >= 0 && iy < p.h;
-      const float* xr = ximg + (long long)(row_ok ? iy : 0) * p.w * p.x_ld;
+      if (interior) {
+        const float* xr = xcol0 + (long long)iy * row_pitch;
 #pragma unroll
-      for (int cidx = 0; cidx < NC; ++cidx) {
-        const ulonglong2* src = (row_ok && col_off[cidx] >= 0) ? reinterpret_cast<const ulonglong2*>(xr + col_off[cidx]) : zeros;
-        dst[cidx] = __ldg(src);
+        for (int cidx = 0; cidx < NC; ++cidx) dst[cidx] = __ldg(reinterpret_cast<const ulonglong2*>(xr + cidx * p.x_ld));
+      } else {
+        const bool row_ok = iy >= 0 && iy < p.h;
+        const float* xr = ximg + (long long)(row_ok ? iy : 0) * row_pitch;
+#pragma unroll
+        for (int cidx = 0; cidx < NC; ++cidx) {
+          const ulonglong2* src = (row_ok && col_off[cidx] >= 0) ? reinterpret_cast<const ulonglong2*>(xr + col_off[cidx]) : zeros;
+          dst[cidx] = __ldg(src);
+        }
       }
     };
     // one output row (2 pixels x 4 channels) from the three buffered input rows
