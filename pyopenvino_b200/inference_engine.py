@@ -657,6 +657,80 @@ class Executable_Network:
         from . import _cabi
         _cabi.call('b200ov_graph_launch', self._graph, C.c_void_p(self.stream.cuda_stream))
 
+    # ---- asynchronous requests (the reference accepts `num_requests` and ignores it, inference_engine.py:86) ----
+    def start_async(self, inputs: dict) -> int:
+        """Queue one inference and return its request id.  Two request slots: the H2D copy of request i+1 runs
+        on a copy stream while request i computes, so a caller that keeps two requests in flight
+        (start_async(i+1) before wait(i)) hides the PCIe transfer behind the kernels.  `inputs` maps input
+        names to host arrays; `request_buffer(slot, name)` gives the slot's pinned staging array for callers
+        that want to fill it in place."""
+        import torch
+        from . import kernels
+        self._ensure_device()
+        if self._graph is None:
+            self.infer(inputs)                     # builds the plan, warms up, captures the graph
+        if not getattr(self, '_requests', None):
+            self._copy_stream = torch.cuda.Stream()
+            self._requests = []
+            for _ in range(2):
+                rq = {'host': {}, 'dev': {}, 'out_host': {}, 'busy': False, 'inputs': None,
+                      'h2d_done': torch.cuda.Event(), 'done': torch.cuda.Event(),
+                      'status': torch.zeros(1, dtype=torch.int32).pin_memory()}
+                for name, st in self._static_in.items():
+                    rq['host'][name] = torch.empty_like(st['host']).pin_memory()
+                    rq['dev'][name] = torch.empty_like(st['dev'].t)
+                for name, arr in self._static_out.items():
+                    rq['out_host'][name] = torch.empty(max(arr.size, 1), dtype=torch.float32).pin_memory()
+                self._requests.append(rq)
+            self._next_request = 0
+        slot = self._next_request
+        self._next_request ^= 1
+        rq = self._requests[slot]
+        if rq['busy']:
+            rq['done'].synchronize()               # the slot's previous request must have drained
+        rq['inputs'] = dict(inputs)
+        with torch.cuda.stream(self._copy_stream):
+            for name, st in self._static_in.items():
+                if name not in inputs:
+                    continue
+                staging = rq['host'][name].numpy()
+                a = np.asarray(inputs[name])
+                if not (a.dtype == np.float32 and a.size == staging.size and
+                        a.__array_interface__['data'][0] == staging.__array_interface__['data'][0]):
+                    a = np.asarray(inputs[name], dtype=np.float32).reshape(-1)
+                    assert a.size == staging.size, 'input {} has {} elements, network expects {}'.format(name, a.size, staging.size)
+                    staging[:] = a
+                rq['dev'][name].copy_(rq['host'][name], non_blocking=True)
+            rq['h2d_done'].record(self._copy_stream)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(rq['h2d_done'])
+            kernels.status_reset()
+            for name, st in self._static_in.items():
+                st['dev'].t.copy_(rq['dev'][name], non_blocking=True)          # D2D into the graph's input buffer
+            self.replay()
+            for name, arr in self._static_out.items():
+                rq['out_host'][name][:arr.size].copy_(arr.t[:arr.size], non_blocking=True)
+            kernels.status_fetch(rq['status'])
+            rq['done'].record(self.stream)
+        rq['busy'] = True
+        return slot
+
+    def request_buffer(self, slot: int, name: str):
+        """Pinned host ndarray (IR shape) of request slot `slot` for input `name` (available after the first start_async)."""
+        st = self._static_in[name]
+        return self._requests[slot]['host'][name].numpy().reshape(tuple(st['node']['data']['shape']))
+
+    def wait(self, slot: int) -> dict:
+        """Block until request `slot` has finished and return {result_name: ndarray}."""
+        rq = self._requests[slot]
+        rq['done'].synchronize()
+        rq['busy'] = False
+        if int(rq['status'][0]) != 0:
+            import torch
+            with torch.cuda.stream(self.stream):
+                return self._infer_full_range(rq['inputs'])
+        return {name: rq['out_host'][name][:arr.size].numpy().reshape(arr.shape).copy() for name, arr in self._static_out.items()}
+
     def _infer_full_range(self, inputs: dict, verbose: bool = False):
         """The f16x2 contractions saw a non-finite output: an operand left the FP16 range (|v| > 65504) or the
         data holds inf / NaN.  Repeat this inference eagerly with the FP32-range kernels (3xTF32 / FFMA), whose

@@ -48,12 +48,15 @@ def status_reset():
     _cabi.call('b200ov_status_reset', _s())
 
 
-def status_fetch():
-    """Queue a D2H copy of the status word into pinned memory; read `status_value()` after a stream sync."""
+def status_fetch(into=None):
+    """Queue a D2H copy of the status word into pinned memory (`into`: a pinned int32 tensor, default the shared
+    one read by `status_value()`); valid after a stream sync."""
     global _status_host
-    if _status_host is None:
-        _status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-    _cabi.call('b200ov_status_fetch', C.c_void_p(_status_host.data_ptr()), _s())
+    if into is None:
+        if _status_host is None:
+            _status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        into = _status_host
+    _cabi.call('b200ov_status_fetch', C.c_void_p(into.data_ptr()), _s())
 
 
 def status_value():

@@ -210,3 +210,21 @@ def test_range_fallback_end_to_end(model_dir):
     again = exe.infer({name: x})[out]       # the graph path is intact afterwards
     assert exe.range_fallbacks == 1
     assert np.all(np.isfinite(again))
+
+
+def test_async_requests_match_sync_infer(model_dir):
+    """start_async / wait with two requests in flight returns what infer() returns for the same inputs."""
+    from tools.synth_bin import synth_input
+    net, exe = _load(model_dir, 'mnist_bn', batch=4)
+    name, out = net.inputs[0]['name'], net.outputs[0]['name']
+    xs = [synth_input('mnist_bn', batch=4, seed=20 + i) for i in range(5)]
+    want = [exe.infer({name: x})[out] for x in xs]
+    got, pending = [], None
+    for x in xs:
+        slot = exe.start_async({name: x})
+        if pending is not None:
+            got.append(exe.wait(pending)[out])
+        pending = slot
+    got.append(exe.wait(pending)[out])
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
