@@ -109,6 +109,20 @@ int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int
 int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias,
                   float* y, void* stream);
 
+/* Sibling convolutions that read the same feature map with the same geometry (the 1x1 / 3x3_reduce / 5x5_reduce
+ * branches of an inception module) as ONE contraction: `w_packed` / `bias` are the packed form of the weights
+ * concatenated along C_out, each member starting at a column that is a multiple of 32 (zero rows / zeros in the gaps),
+ * d->cout = width of that fused matrix (d->y_ld is ignored).  Output columns [col0, col0 + cout) go to tensor `y`
+ * with channel pitch `y_ld`.  1..3 segments; needs the B200OV_MATH_F16X2 path (B200OV_ERR_UNSUPPORTED otherwise,
+ * the caller then issues the members one by one).  Replaces the corresponding Convolution.compute calls
+ * (Convolution.py:149-176) + Add + ReLU. */
+typedef struct {
+  void* y;
+  int32_t col0, cout, y_ld;
+} b200ov_conv_seg;
+int b200ov_conv2d_multi(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias,
+                        int nseg, const b200ov_conv_seg* segs, void* stream);
+
 /* Y[m][n] = act(sum_k A[m][k] * Bkn[k][n] + bias[n]); Bkn is the packed form of a 1x1 conv weight
  * (b200ov_pack_conv_weights with kh = kw = 1 on B[n][k]).  Replaces MatMul.compute for
  * transpose_a=false / transpose_b=true (MatMul.py:9-17); other flag combinations are brought to

@@ -34,6 +34,10 @@ class DwConvDesc(C.Structure):
 DW_AUTO, DW_EXACT = 0, 1
 
 
+class ConvSeg(C.Structure):
+    _fields_ = [('y', C.c_void_p), ('col0', C.c_int32), ('cout', C.c_int32), ('y_ld', C.c_int32)]
+
+
 class PoolDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'pb', 'pr', 'oh', 'ow',
                                          'x_ld', 'y_ld', 'mode')]
@@ -69,6 +73,7 @@ SIGNATURES = {
     'b200ov_conv_weight_dims': [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)],
     'b200ov_pack_conv_weights': [_P, _P, _I, _I, _I, _I, _P],
     'b200ov_conv2d': [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
+    'b200ov_conv2d_multi': [C.POINTER(ConvDesc), _P, _P, _P, _I, C.POINTER(ConvSeg), _P],
     'b200ov_matmul': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P],
     'b200ov_status_word': [C.POINTER(C.c_void_p)],
     'b200ov_status_reset': [_P],
@@ -90,7 +95,7 @@ NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
 _lib = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
-_LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_matmul', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
+_LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
               'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_transpose',
               'b200ov_nchw_to_nhwc_affine', 'b200ov_copy2d', 'b200ov_detection_output'}
 

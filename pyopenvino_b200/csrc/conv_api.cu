@@ -9,6 +9,8 @@ int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, c
 // persistent tcgen05 FP16-split path (conv_f16x2.cu)
 bool f16x2_eligible(const b200ov_conv_desc* d, const float* x);
 int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s);
+int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
+                       const b200ov_conv_seg* segs, cudaStream_t s);
 unsigned int* f16x2_status_word();
 bool has_tf32_section(int cin);
 void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* kpad);
@@ -74,6 +76,19 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
     default:
       return set_error(B200OV_ERR_INVALID, "conv2d: unknown math mode %d", d->math);
   }
+}
+
+int b200ov_conv2d_multi(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias, int nseg,
+                        const b200ov_conv_seg* segs, void* stream) {
+  B200OV_REQUIRE(d && x && w_packed && segs, "conv2d_multi: null argument");
+  B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 &&
+                     d->pt >= 0 && d->pl >= 0 && d->oh > 0 && d->ow > 0 && d->x_ld >= d->cin,
+                 "conv2d_multi: bad geometry");
+  B200OV_REQUIRE(d->ldw >= d->cout && d->ldw % 64 == 0, "conv2d_multi: weights are not in packed form (ldw %d)", d->ldw);
+  B200OV_REQUIRE(d->act >= B200OV_ACT_NONE && d->act <= B200OV_ACT_CLAMP, "conv2d_multi: bad activation");
+  if (d->math != B200OV_MATH_AUTO && d->math != B200OV_MATH_F16X2)
+    return set_error(B200OV_ERR_UNSUPPORTED, "conv2d_multi: only the f16x2 path supports several output tensors");
+  return conv2d_f16x2_multi(d, x, f16_section(d, w_packed), bias, nseg, segs, as_stream(stream));
 }
 
 int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw, const float* bias,

@@ -80,7 +80,12 @@ struct Params {
   int M, num_slots, units, tiles_n, num_tiles;
   int act;
   float lo, hi;
-  int tma_store;                       // 1: output written by TMA (y 16-byte aligned, y_ld % 4 == 0)
+  int tma_store;                       // 1: output written by TMA (every y 16-byte aligned, y_ld % 4 == 0)
+  // output segments: fused columns [seg_col0, seg_col0 + seg_cout) go to tensor seg_y (pitch seg_yld); seg_col0 is a
+  // multiple of 32.  One segment for an ordinary convolution, up to three for sibling 1x1 convolutions run as one GEMM.
+  int nseg;
+  int seg_col0[3], seg_cout[3], seg_yld[3];
+  float* seg_y[3];
   int wide_loads;                      // 1: 256-bit gathers (x 32-byte aligned, x_ld % 8 == 0)
   int pair4;                           // 1: cin <= 4 with a pixel pitch of 4 floats: a unit is two horizontally
                                        //    adjacent filter taps x 4 channels (d_upt then divides by units per filter ROW)
@@ -188,9 +193,10 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
 
 template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
-                  const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y) {
+                  const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y0,
+                  const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2) {
   using L = Smem<BLOCK_N, SB>;
   constexpr int A_SLOTS = a_slots(BLOCK_N);
   constexpr int A_COL0 = a_col0(BLOCK_N);
@@ -231,7 +237,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     fence_mbar_init();
     prefetch_tensormap(&map_hi);
     prefetch_tensormap(&map_lo);
-    prefetch_tensormap(&map_y);
+    prefetch_tensormap(&map_y0);
   }
   if (warp == 1) tmem_alloc(base + L::TMEM_PTR, 512);
   tc_fence_before();
@@ -513,14 +519,26 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
             *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
           }
         }
+        // which output tensor a 32-column block belongs to (segments start at multiples of 32 columns)
+        auto segment_of = [&](int nb, int& local) -> int {
+          int sg = -1;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < p.nseg && nb >= p.seg_col0[i] && nb < p.seg_col0[i] + p.seg_cout[i]) { sg = i; local = nb - p.seg_col0[i]; }
+          return sg;
+        };
         if (p.tma_store) {
           fence_proxy_async();
           __syncwarp();
           if (elect_one_sync()) {
 #pragma unroll
             for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
-              const int nb = n0 + (round * L::STG_BLOCKS + sb) * 32;
-              if (nb < p.cout && m0 + 32 * q < p.M) tma_store_2d(&map_y, stage_u32 + sb * 4096, nb, m0 + 32 * q);
+              int local = 0;
+              const int sg = segment_of(n0 + (round * L::STG_BLOCKS + sb) * 32, local);
+              if (sg >= 0 && m0 + 32 * q < p.M) {
+                const CUtensorMap* mp = sg == 0 ? &map_y0 : (sg == 1 ? &map_y1 : &map_y2);
+                tma_store_2d(mp, stage_u32 + sb * 4096, local, m0 + 32 * q);
+              }
             }
             tma_store_commit();
           }
@@ -529,11 +547,16 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           __syncwarp();
 #pragma unroll
           for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
-            const int n = n0 + (round * L::STG_BLOCKS + sb) * 32 + lane;
+            int local = 0;
+            const int sg = segment_of(n0 + (round * L::STG_BLOCKS + sb) * 32, local);
+            if (sg < 0) continue;
+            const int n = local + lane;
+            float* ys = p.seg_y[sg];
+            const int yld = p.seg_yld[sg], ncout = p.seg_cout[sg];
             for (int r = 0; r < 32; ++r) {
               const int m = m0 + 32 * q + r;
               const float v = *reinterpret_cast<const float*>(stage_ptr + sb * 4096 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-              if (m < p.M && n < p.cout) y[(long long)m * p.y_ld + n] = v;
+              if (m < p.M && n < ncout) ys[(long long)m * yld + n] = v;
             }
           }
           __syncwarp();
@@ -616,8 +639,8 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
 }
 
 template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
-static int launch(const Params& p, const float* x, const float* bias, float* y, unsigned int* status, const CUtensorMap& mh,
-                  const CUtensorMap& ml, const CUtensorMap& my, cudaStream_t s) {
+static int launch(const Params& p, const float* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
+                  const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s) {
   using L = Smem<BLOCK_N, SB>;
   auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR>;
   static bool configured = false;
@@ -626,7 +649,7 @@ static int launch(const Params& p, const float* x, const float* bias, float* y, 
     configured = true;
   }
   const int grid = p.num_tiles < props().sm_count ? p.num_tiles : props().sm_count;
-  kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(p, x, bias, y, status, mh, ml, my);
+  kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(p, x, bias, status, mh, ml, my[0], my[1], my[2]);
   B200OV_LAUNCH_CHECK("conv_f16x2_kernel");
   return B200OV_OK;
 }
@@ -683,10 +706,13 @@ unsigned int* f16x2_status_word() {
   return p;
 }
 
-// `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.
-int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
+// `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.  d->cout is the width of the
+// (fused) weight matrix; the output columns are routed to `nseg` tensors.
+int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
+                       const b200ov_conv_seg* segs, cudaStream_t s) {
   if (!f16x2_eligible(d, x))
     return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with cin %% 8 == 0 (or cin <= 4 at a pixel pitch of 4) and no fused Sigmoid");
+  if (nseg < 1 || nseg > 3) return set_error(B200OV_ERR_INVALID, "conv2d: 1..3 output segments");
   f16::Params p;
   memset(&p, 0, sizeof(p));
   p.h = d->h; p.w = d->w; p.cin = d->cin; p.cout = d->cout; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.pl = d->pl;
@@ -695,6 +721,15 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
   if (M > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: too many output pixels");
   p.M = (int)M;
   if (p.M == 0) return B200OV_OK;
+  p.nseg = nseg;
+  p.tma_store = 1;
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].y == nullptr || segs[i].cout <= 0 || segs[i].col0 < 0 || segs[i].col0 % 32 != 0 || segs[i].col0 + segs[i].cout > d->cout ||
+        segs[i].y_ld < segs[i].cout)
+      return set_error(B200OV_ERR_INVALID, "conv2d: bad output segment %d", i);
+    p.seg_col0[i] = segs[i].col0; p.seg_cout[i] = segs[i].cout; p.seg_yld[i] = segs[i].y_ld; p.seg_y[i] = static_cast<float*>(segs[i].y);
+    if (segs[i].y_ld % 4 != 0 || !aligned16(segs[i].y)) p.tma_store = 0;
+  }
   int coutp, kpad, upt, units;
   f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
   p.units = units;
@@ -705,45 +740,40 @@ int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, con
   if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
   p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
-  p.tma_store = (d->y_ld % 4 == 0) && aligned16(y);
   p.pair4 = d->cin <= 4;
   p.wide_loads = !p.pair4 && (d->x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(d->kw);
   p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
   const __half* hi_plane = reinterpret_cast<const __half*>(wt);
   const __half* lo_plane = hi_plane + (long long)coutp * kpad;
-  CUtensorMap mh, ml, my;
+  CUtensorMap mh, ml, my[3];
   int rc = f16::make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
   if (rc) return rc;
   rc = f16::make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
   if (rc) return rc;
-  if (p.tma_store) {
-    rc = f16::make_map_2d(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, d->cout, p.M, (long long)d->y_ld * 4, 32, 32);
-    if (rc) return rc;
-  } else {
-    my = mh;       // never dereferenced
+  for (int i = 0; i < 3; ++i) {
+    if (p.tma_store && i < nseg) {
+      rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, segs[i].cout, p.M, (long long)segs[i].y_ld * 4, 32, 32);
+      if (rc) return rc;
+    } else {
+      my[i] = mh;    // never dereferenced
+    }
   }
   unsigned int* status = f16x2_status_word();
-  static int sb128 = -1;      // developer knob: B ring depth of the 128-wide tile (B200OV_F16_SB = 3..6)
-  if (sb128 < 0) {
-    const char* e = getenv("B200OV_F16_SB");
-    sb128 = e ? atoi(e) : 4;
-    if (sb128 < 2 || sb128 > 6) sb128 = 4;
-  }
 #define B200OV_F16_LAUNCH(N_, SB_) \
-  (p.pair4 ? f16::launch<N_, SB_, false, true>(p, x, bias, y, status, mh, ml, my, s) \
-           : p.wide_loads ? f16::launch<N_, SB_, true, false>(p, x, bias, y, status, mh, ml, my, s) \
-                          : f16::launch<N_, SB_, false, false>(p, x, bias, y, status, mh, ml, my, s))
-  if (block_n == 128) {
-    if (sb128 == 2) return B200OV_F16_LAUNCH(128, 2);
-    if (sb128 == 3) return B200OV_F16_LAUNCH(128, 3);
-    if (sb128 == 5) return B200OV_F16_LAUNCH(128, 5);
-    if (sb128 == 6) return B200OV_F16_LAUNCH(128, 6);
-    return B200OV_F16_LAUNCH(128, 4);
-  }
+  (p.pair4 ? f16::launch<N_, SB_, false, true>(p, x, bias, status, mh, ml, my, s) \
+           : p.wide_loads ? f16::launch<N_, SB_, true, false>(p, x, bias, status, mh, ml, my, s) \
+                          : f16::launch<N_, SB_, false, false>(p, x, bias, status, mh, ml, my, s))
+  if (block_n == 128) return B200OV_F16_LAUNCH(128, 4);
   if (block_n == 64) return B200OV_F16_LAUNCH(64, 6);
   return B200OV_F16_LAUNCH(32, 6);
 #undef B200OV_F16_LAUNCH
+}
+
+int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
+  b200ov_conv_seg seg;
+  seg.y = y; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = d->y_ld;
+  return conv2d_f16x2_multi(d, x, wt, bias, 1, &seg, s);
 }
 
 }  // namespace b200ov

@@ -410,6 +410,32 @@ class Executable_Network:
                 if G.nodes[head]['type'] in ('ReLU', 'Clamp', 'Sigmoid', 'LRN') and head != tail_id:
                     continue
                 plan[head]['out_slot'] = (n, coff, c)
+        # Sibling 1x1 convolutions (same input, stride 1, no padding, bias + the same activation): one contraction
+        # with several output tensors -- the 1x1 / 3x3_reduce / 5x5_reduce branches of an inception module read
+        # (and FP16-split) their common input once instead of three times.
+        groups = {}
+        for n in (self.task_list if os.environ.get('B200OV_NO_GROUP') != '1' else []):
+            node = G.nodes[n]
+            if node['type'] != 'Convolution' or plan[n]['skip']:
+                continue
+            d = node['data']
+            wdims = node['input'][1]['dims']
+            if tuple(wdims[2:]) != (1, 1) or common_def.string_to_tuple(d['strides']) != (1, 1) or \
+                    common_def.string_to_tuple(d['pads_begin']) != (0, 0) or common_def.string_to_tuple(d['pads_end']) != (0, 0) or \
+                    common_def.string_to_tuple(d['dilations']) != (1, 1) or wdims[1] % 8 != 0:
+                continue
+            src = next(((fl, fp) for fl in G.pred[n] for (_fl, fp, _tl, tp) in [G.edges[(fl, n)]['connection']] if tp == 0), None)
+            wsrc = next((fl for fl in G.pred[n] if G.edges[(fl, n)]['connection'][3] == 1), None)
+            if src is None or wsrc is None or G.nodes[wsrc]['type'] != 'Const':
+                continue
+            groups.setdefault((src, plan[n]['ops'].get('act'), 'bias' in plan[n]['ops']), []).append(n)
+        for members in groups.values():
+            for i in range(0, len(members) - 1, 3):
+                chunk = members[i:i + 3]
+                if len(chunk) >= 2:
+                    plan[chunk[0]]['group'] = chunk
+                    for m in chunk[1:]:
+                        plan[m]['grouped'] = chunk[0]
         self._plan = plan
         return plan
 
@@ -431,11 +457,19 @@ class Executable_Network:
         p = self.ienet.ie.plugins
         plan = self._plan if self._plan is not None else self.build_plan()
         concat_bufs = {}
+        group_done = set()
         for task in self.task_list:
             node = G.nodes[task]
             step = plan[task]
             if step['skip']:
                 continue
+            if task in group_done:
+                continue
+            if step.get('group') and self.kernel_type not in ('fp32', 'tf32x3', 'tf32', 'safe', 'f16x2') and \
+                    kernels.default_math == kernels._cabi.MATH_AUTO and self.expected_result is None and not self.pickle_node_args:
+                if self._run_group(step['group'], concat_bufs):
+                    group_done.update(step['group'])
+                    continue
             node_type = node['type']
             if node_type not in p.plugins:
                 print('ERROR: Operation \'{}\' (node={}) is not supported.'.format(node_type, node['name']))
@@ -506,6 +540,43 @@ class Executable_Network:
                 for port_id, data in res.items():
                     tport = port_id if step['store_as'] == task else common_def.first_output_port(target)
                     target['output'][tport]['data'] = data
+
+    def _run_group(self, members, concat_bufs):
+        """Sibling 1x1 convolutions as one multi-output contraction.  False -> run the members one by one."""
+        from . import kernels
+        from .device import is_device
+        G = self.ienet.G
+        plan = self._plan
+        first = G.nodes[members[0]]
+        x = self.prepare_inputs_for_task(members[0])[0]
+        if not is_device(x) or x.layout != 'nhwc':
+            return False
+        specs, act = [], plan[members[0]]['ops'].get('act')
+        for m in members:
+            node, st = G.nodes[m], plan[m]
+            ins = self.prepare_inputs_for_task(m)
+            bias = G.nodes[st['ops']['bias']]['output'][0]['data'] if 'bias' in st['ops'] else None
+            out = None
+            if st['out_slot'] is not None:
+                cid, coff, c = st['out_slot']
+                if cid not in concat_bufs:
+                    n_, c_, h_, w_ = G.nodes[cid]['output'][common_def.first_output_port(G.nodes[cid])]['dims']
+                    concat_bufs[cid] = kernels.new_nhwc(n_, c_, h_, w_)
+                out = kernels.channel_slice(concat_bufs[cid], coff, c)
+            specs.append((ins[1], bias, out))
+        ev = None
+        if self._step_events is not None:
+            import torch
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        outs = kernels.conv1x1_group(x, specs, act=act)
+        if ev is not None:
+            ev[1].record()
+            self._step_events.append((members[0], ev[0], ev[1]))
+        for m, y in zip(members, outs):
+            target = G.nodes[plan[m]['store_as']]
+            target['output'][common_def.first_output_port(target)]['data'] = y
+        return True
 
     def run_tasks(self, verbose: bool = False):
         """Eager pass: every scheduled node through its plugin (inference_engine.py:259-292)."""

@@ -215,6 +215,49 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
     return out
 
 
+def conv1x1_group(x, members, act=None):
+    """Sibling 1x1 convolutions of one feature map as a single contraction (b200ov_conv2d_multi).
+    members = [(w OIHW DeviceArray, bias DeviceArray | None, out DeviceArray | None), ...] (2 or 3).
+    Returns the list of outputs.  The fused weight matrix (members concatenated along C_out, each starting at a
+    multiple of 32 columns) is built and packed once and cached on the first member's weight."""
+    x = as_nhwc(x)
+    n, c, h, wd = x.shape
+    ws = [as_device(m[0]) for m in members]
+    key = ('group',) + tuple(id(w.t) for w in ws)
+    cache = ws[0].cache
+    if cache.get('group_key') != key:
+        col0s, total = [], 0
+        for w in ws:
+            assert w.ndim == 4 and w.shape[1] == c and w.shape[2] == 1 and w.shape[3] == 1
+            col0s.append(total)
+            total += (w.shape[0] + 31) // 32 * 32
+        fw = torch.zeros(total * c, dtype=torch.float32, device='cuda')
+        fb = torch.zeros(total, dtype=torch.float32, device='cuda')
+        for (w, (_, b, _o), col0) in zip(ws, members, col0s):
+            co = w.shape[0]
+            fw.view(total, c)[col0:col0 + co].copy_(w.t[:co * c].view(co, c))
+            if b is not None:
+                bd = as_device(b)
+                fb[col0:col0 + co].copy_(bd.t[:co])
+        pk = pack_conv(DeviceArray(fw, (total, c, 1, 1), 'plain'))
+        cache['group_key'] = key
+        cache['group'] = (pk, DeviceArray(fb, (total,), 'plain'), col0s, total)
+    pk, fb, col0s, total = cache['group']
+    outs = []
+    segs = (_cabi.ConvSeg * len(members))()
+    for i, (w, (_, _b, o)) in enumerate(zip(ws, members)):
+        shape = (n, w.shape[0], h, wd)
+        o = _check_out(o, shape) if o is not None else new_nhwc(*shape)
+        outs.append(o)
+        segs[i].y = o.ptr
+        segs[i].col0, segs[i].cout, segs[i].y_ld = col0s[i], w.shape[0], o.ld
+    code, lo, hi = _act(act)
+    d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=total, kh=1, kw=1, sh=1, sw=1, pt=0, pl=0, oh=h, ow=wd, x_ld=x.ld, y_ld=total,
+                       ldw=pk.ldw, act=code, act_lo=lo, act_hi=hi, math=_cabi.MATH_AUTO)
+    _cabi.call('b200ov_conv2d_multi', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(fb), len(members), segs, _s())
+    return outs
+
+
 def matmul(a, b, transpose_a=False, transpose_b=True, bias=None, act=None, math=None):
     a = as_plain(a)
     assert a.ndim == 2

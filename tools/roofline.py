@@ -65,6 +65,16 @@ def layer_work(exe):
             nbytes = 0        # NHWC-resident: metadata only for the [0,2,3,1] permutation
             kind = 'transpose'
         work[n] = {'flops': int(flops), 'bytes': int(nbytes), 'kind': kind, 'type': t, 'name': node['name']}
+    # sibling 1x1 convolutions run as one contraction: their work is accounted on the group head (the shared
+    # input is read once)
+    for n in list(work):
+        head = plan[n].get('grouped')
+        if head is not None and head in work:
+            x_bytes = 4 * _numel(G.nodes[n]['input'][0]['dims'])
+            work[head]['flops'] += work[n]['flops']
+            work[head]['bytes'] += work[n]['bytes'] - x_bytes
+            work[head]['name'] += ' + ' + work[n]['name'].split('/')[-2] if '/' in work[n]['name'] else ''
+            del work[n]
     return work
 
 
