@@ -227,3 +227,26 @@ def test_f16x2_range_overflow_falls_back_to_full_range(plugins):
     assert ok, msg
     pinned = plugins['Convolution'].compute(node, {0: x, 1: w}, kernel_type='f16x2')[2]
     assert not np.all(np.isfinite(pinned))
+
+
+def test_sibling_1x1_group_matches_separate_convs(plugins):
+    """b200ov_conv2d_multi: three 1x1 convolutions of one feature map as a single contraction, one of them
+    writing into a channel slice of a wider (Concat) buffer; every output must match the oracle."""
+    from oracle import ref_ops
+    from pyopenvino_b200 import kernels
+    rng = np.random.default_rng(11)
+    n, cin, hw = 3, 192, 28
+    couts = (64, 96, 16)
+    x = np.maximum(rng.standard_normal((n, cin, hw, hw)), 0).astype(np.float32)
+    ws = [(rng.standard_normal((co, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float32) for co in couts]
+    bs = [(0.05 * rng.standard_normal((1, co, 1, 1))).astype(np.float32) for co in couts]
+    xd = kernels.to_nhwc(kernels.upload(x))
+    concat = kernels.new_nhwc(n, 256, hw, hw)
+    members = [(kernels.upload(ws[0]), kernels.upload(bs[0]), kernels.channel_slice(concat, 64, 64)),
+               (kernels.upload(ws[1]), kernels.upload(bs[1]), None), (kernels.upload(ws[2]), kernels.upload(bs[2]), None)]
+    outs = kernels.conv1x1_group(xd, members, act=('relu',))
+    for w, b, y in zip(ws, bs, outs):
+        want = np.maximum(ref_ops.conv_special(x, w, (1, 1), (0, 0), (0, 0), 'explicit') + b, 0)
+        ok, msg = close(y.numpy(), want)
+        assert ok, msg
+    assert outs[0].ld == 256 and outs[0].c_off == 64
