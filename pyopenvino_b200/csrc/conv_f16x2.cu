@@ -14,20 +14,20 @@
 // units of 8 channels of one filter tap (cin padded to 8), 4 units = one 32-wide "slot".
 //
 // Warp roles (512 threads = 4 warpgroups with setmaxnreg budgets, one persistent CTA per SM, static tile schedule):
-//   warp 0      B loader : TMA loads of the pre-split FP16 weight tiles (hi / lo planes, 64 K-elements per
+//   warp 12     B loader : TMA loads of the pre-split FP16 weight tiles (hi / lo planes, 64 K-elements per
 //                          stage, 128B swizzle) into a shared-memory ring.
-//   warp 1      MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
+//   warp 13     MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
 //                          shared memory; tcgen05.commit releases A slots / B stages / accumulators.
-//   warp 2      gate     : waits on every mbarrier a slot depends on, ahead of the MMA warp, and publishes a
+//   warp 14     gate     : waits on every mbarrier a slot depends on, ahead of the MMA warp, and publishes a
 //                          "slots ready" counter (the MMA issue blocks on the tensor-pipe queue, so its own
 //                          waits must be short).
-//   warps 4-11  A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
+//   warps 0-7   A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
 //                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split with packed
 //                          FP32 math, and tcgen05.st into a 4-slot TMEM ring.  Two sets of four warps work on
 //                          alternating pairs of slots, running ahead across tile boundaries.  The A operand
 //                          never touches shared memory: the MMA reads of B alone already use ~60% of the
 //                          128 B/clk shared-memory port.
-//   warps 12-15 epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
+//   warps 8-11  epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
 //                          see below), add the cross terms, bias, activation, stage the tile in shared memory
 //                          and write it with TMA stores (coalesced, asynchronous), overlapping the next tile.
 //
@@ -69,6 +69,13 @@ constexpr int NUM_SETS = 2;             // producer warp sets
 constexpr int SET_THREADS = 128;       // threads that build one A slot
 constexpr int NUM_EPILOGUE = 128;
 constexpr int NUM_THREADS = 128 + NUM_SETS * SET_THREADS + NUM_EPILOGUE;      // 512: four warpgroups
+// Warp numbering: the SM sub-partition arbiter prefers the HIGHEST warp id among eligible warps, so the three control
+// warps (they issue little but everything waits on them) sit at the top and the arithmetic-heavy producers at the
+// bottom.  With the control warps in warps 0-2 the gate needed 500-900 cycles to forward one barrier and the MMA warp
+// ~300 cycles between two slots (timeline trace, tools/f16_trace.py).
+constexpr int W_PRODUCER0 = 0;                               // warps 0-7  : producer sets (warpgroups 0, 1)
+constexpr int W_EPILOGUE0 = 4 * NUM_SETS;                    // warps 8-11 : epilogue (warpgroup 2)
+constexpr int W_TMA = W_EPILOGUE0 + 4, W_MMA = W_TMA + 1, W_GATE = W_TMA + 2;    // warpgroup 3: 12, 13, 14 (15 idle)
 // register budget per warpgroup (setmaxnreg): 40 + 2 * 136 + 200 = 512 = 4 * 128 (the launch allocation)
 constexpr int REGS_CONTROL = 40, REGS_PRODUCER = 136, REGS_EPILOGUE = 200;
 constexpr int EPI_BAR_ID = 1;
@@ -97,6 +104,10 @@ __device__ __align__(32) float g_zero_run[8];      // source of the np.pad zeros
 #ifdef B200OV_F16_TRACE
 // developer-only (build with B200OV_EXTRA_NVCC_FLAGS=-DB200OV_F16_TRACE): cycles CTA 0 spends in each wait, per role
 __device__ long long g_f16_trace[4][8];
+// per-item timeline of CTA 0 (first 128 items): [event][item], events: 0 loads issued, 1 slot free (a_empty passed),
+// 2 published (a_full arrive), 3 gate published ready, 4 MMA issue start, 5 MMA issue end, 6 epilogue got chunk, 7 epilogue released chunk
+__device__ long long g_f16_timeline[8][128];
+#define F16_STAMP(ev, idx) do { if (blockIdx.x == 0 && (idx) < 128) g_f16_timeline[ev][idx] = clock64(); } while (0)
 #define F16_TRACE_DECL long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start_ = clock64();
 #define F16_WAIT(k, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); tr_[k] += clock64() - t0_; } while (0)
 #define F16_TIMED(k, stmt) do { const long long t0_ = clock64(); stmt; tr_[k] += clock64() - t0_; } while (0)
@@ -106,6 +117,7 @@ __device__ long long g_f16_trace[4][8];
 #define F16_WAIT(k, bar, par) mbar_wait(bar, par)
 #define F16_TIMED(k, stmt) stmt
 #define F16_TRACE_STORE(role, cond)
+#define F16_STAMP(ev, idx)
 #endif
 
 template <int BLOCK_N, int SB>
@@ -239,7 +251,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     prefetch_tensormap(&map_lo);
     prefetch_tensormap(&map_y0);
   }
-  if (warp == 1) tmem_alloc(base + L::TMEM_PTR, 512);
+  if (warp == W_MMA) tmem_alloc(base + L::TMEM_PTR, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -248,10 +260,10 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
   const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int num_stages = (p.num_slots + 1) >> 1;      // B stages per tile
 
-  if (warp < 4) {
-    // warpgroup 0: B loader (warp 0), MMA issuer (warp 1), gate (warp 2), one idle warp.  Hand the registers to the others.
+  if (warp >= W_TMA) {
+    // control warpgroup: B loader, MMA issuer, gate, one idle warp.  Hand the registers to the others.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
-    if (warp == 0) {
+    if (warp == W_TMA) {
       // ================= B loader ====================================================================
       {
         F16_TRACE_DECL
@@ -272,53 +284,82 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         }
         F16_TRACE_STORE(0, lane == 0);
       }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
       // ================= MMA issuer ==================================================================
       constexpr uint32_t idesc = instr_desc(BLOCK_N);
       const uint32_t tmem_cross = tmem_base + NBUF * BLOCK_N;
-      uint32_t acount = 0, bcount = 0, chunkcount = 0;
       F16_TRACE_DECL
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        for (int slot = 0; slot < p.num_slots; ++slot) {
+      // One elected lane runs the whole loop.  The issue of a UTCHMMA blocks while the tensor-pipe queue is full, so
+      // everything else this thread does per slot (addresses of the next slot, its ready poll) is placed BETWEEN the two
+      // K steps of the current slot, when the queue is fullest, and the descriptors are derived from two values built once.
+      if (elect_one_sync()) {
+        const uint64_t desc_hi0 = make_smem_desc_sw128(base + L::B_HI), desc_lo0 = make_smem_desc_sw128(base + L::B_LO);
+        struct Slot {
+          uint32_t a_hi, tmem_main, acc_main, acc_cross, bar_a, bar_b, bar_main;
+          uint64_t b_hi, b_lo;
+          bool commit_b, commit_main, commit_cross;
+        };
+        int tl = 0, slot = 0;
+        uint32_t acount = 0, bcount = 0, chunkcount = 0;
+        const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
+        auto prep = [&](Slot& o) {                   // describe item (tl, slot), then advance the counters
           const bool last = slot == p.num_slots - 1;
-          const int buf = chunkcount % NBUF;
-          const int bs = bcount % SB;
-          const int as = acount % A_SLOTS;
-          // all inputs of this slot (accumulators drained, B stage landed, A slot written) were awaited by the
-          // gate warp; a shared-memory counter costs one ~30-cycle load here instead of four mbarrier try_waits
-          F16_TIMED(3, wait_ready(base + L::READY, acount + 1));
-          F16_TIMED(4, tc_fence_after());
+          const int buf = chunkcount % NBUF, bs = bcount % SB, as = acount % A_SLOTS;
+          const uint64_t off = (uint64_t)((bs * L::B_PLANE_BYTES + (slot & 1) * 64) >> 4);   // stage + second slot of the stage (+64 B along K)
+          o.a_hi = tmem_base + A_COL0 + as * 32;
+          o.tmem_main = tmem_base + buf * BLOCK_N;
+          o.acc_main = slot % CHUNK > 0 ? 1u : 0u;
+          o.acc_cross = slot > 0 ? 1u : 0u;
+          o.b_hi = desc_hi0 + off;
+          o.b_lo = desc_lo0 + off;
+          o.bar_a = bar_a_empty(as); o.bar_b = bar_b_empty(bs); o.bar_main = bar_main_full(buf);
+          o.commit_b = (slot & 1) || last;
+          o.commit_main = slot % CHUNK == CHUNK - 1 || last;
+          o.commit_cross = last;
+          ++acount;
+          if (o.commit_b) ++bcount;
+          if (o.commit_main) ++chunkcount;
+          if (last) { slot = 0; ++tl; } else { ++slot; }
+        };
+        Slot cur, nxt;
+        if (total_items > 0) {
+          prep(cur);
+          F16_TIMED(3, wait_ready(base + L::READY, 1));
+          tc_fence_after();
+        }
+        for (uint32_t it = 0; it < total_items; ++it) {
 #ifdef B200OV_F16_TRACE
           const long long t_issue0_ = clock64();
+          F16_STAMP(4, it);
 #endif
-          if (elect_one_sync()) {
-            const uint32_t a_hi = tmem_base + A_COL0 + as * 32, a_lo = a_hi + 16;
-            const uint64_t koff = (uint64_t)((slot & 1) * 4);                  // second slot of the stage: +64 bytes along K
-            const uint64_t b_hi = make_smem_desc_sw128(base + L::B_HI + bs * L::B_PLANE_BYTES) + koff;
-            const uint64_t b_lo = make_smem_desc_sw128(base + L::B_LO + bs * L::B_PLANE_BYTES) + koff;
-            const uint32_t tmem_main = tmem_base + buf * BLOCK_N;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {                                      // two K = 16 steps per slot
-              umma_f16_ts(tmem_main, a_hi + 8 * k, b_hi + 2 * k, idesc, (slot % CHUNK > 0 || k > 0) ? 1u : 0u);
-              umma_f16_ts(tmem_cross, a_lo + 8 * k, b_hi + 2 * k, idesc, (slot > 0 || k > 0) ? 1u : 0u);
-              umma_f16_ts(tmem_cross, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
-            }
-            umma_commit(bar_a_empty(as));
-            if ((slot & 1) || last) umma_commit(bar_b_empty(bs));
-            if (slot % CHUNK == CHUNK - 1 || last) umma_commit(bar_main_full(buf));
-            if (last) umma_commit(bar_cross_full);
-          }
-          __syncwarp();
+          umma_f16_ts(cur.tmem_main, cur.a_hi, cur.b_hi, idesc, cur.acc_main);
+          umma_f16_ts(tmem_cross, cur.a_hi + 16, cur.b_hi, idesc, cur.acc_cross);
+          umma_f16_ts(tmem_cross, cur.a_hi, cur.b_lo, idesc, 1u);
+          const bool more = it + 1 < total_items;
+          if (more) prep(nxt);
+          umma_f16_ts(cur.tmem_main, cur.a_hi + 8, cur.b_hi + 2, idesc, 1u);
+          umma_f16_ts(tmem_cross, cur.a_hi + 24, cur.b_hi + 2, idesc, 1u);
+          umma_f16_ts(tmem_cross, cur.a_hi + 8, cur.b_lo + 2, idesc, 1u);
+          umma_commit(cur.bar_a);
+          if (cur.commit_b) umma_commit(cur.bar_b);
+          if (cur.commit_main) umma_commit(cur.bar_main);
+          if (cur.commit_cross) umma_commit(bar_cross_full);
 #ifdef B200OV_F16_TRACE
           tr_[5] += clock64() - t_issue0_;
+          F16_STAMP(5, it);
 #endif
-          ++acount;
-          if ((slot & 1) || last) ++bcount;
-          if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
+          if (more) {
+            // all inputs of the next slot (accumulators drained, B stage landed, A slot written) were awaited by the
+            // gate warp; its shared-memory counter costs one short load here instead of four mbarrier try_waits
+            F16_TIMED(3, wait_ready(base + L::READY, it + 2));
+            tc_fence_after();
+            cur = nxt;
+          }
         }
       }
+      __syncwarp();
       F16_TRACE_STORE(1, lane == 0);
-    } else if (warp == 2) {
+    } else if (warp == W_GATE) {
       // ================= gate ========================================================================
       // Runs the MMA warp's waits ahead of it: the UTCHMMA issue blocks while the tensor-pipe queue is full,
       // and four serial mbarrier waits per slot in the issuing thread left the pipe idle half of the time.
@@ -333,19 +374,19 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           ++acount;
           if ((slot & 1) || last) ++bcount;
           if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
-          if (lane == 0) st_release_shared(base + L::READY, acount);
+          if (lane == 0) { st_release_shared(base + L::READY, acount); F16_STAMP(3, acount - 1); }
           __syncwarp();
         }
       }
     }
-  } else if (warp < 4 + 4 * NUM_SETS) {
+  } else if (warp < W_EPILOGUE0) {
     // ================= A producers: gather -> split -> TMEM ==========================================
     // Two sets of four warps; a set owns every other PAIR of consecutive slots ("items").  All loads of a
     // warp share one scoreboard slot, so a register ring inside a warp cannot overlap load latency with
     // the split; the overlap comes from the other set (and the other warps of the SM sub-partition)
     // working on the neighbouring pair in the meantime.
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-    const int set = (warp - 4) >> 2;
+    const int set = (warp - W_PRODUCER0) >> 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int u4 = lane & 3, rsub = lane >> 2;
     const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
@@ -406,6 +447,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
       const int as = item % A_SLOTS;
       F16_WAIT(0, bar_a_empty(as), ((item / A_SLOTS) & 1) ^ 1);
+      if (q == 0 && lane == 0) F16_STAMP(1, item);
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -425,20 +467,22 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
       mbar_arrive(bar_a_full(as));
+      if (q == 0 && lane == 0) F16_STAMP(2, item);
     };
     Run8 d0[4], d1[4];
     for (uint32_t item = 2 * set; item < total_items; item += 2 * NUM_SETS) {
       const bool two = item + 1 < total_items;
       F16_TIMED(1, issue_loads(item, d0); if (two) issue_loads(item + 1, d1));
+      if (q == 0 && lane == 0) { F16_STAMP(0, item); F16_STAMP(0, item + 1); }
       F16_TIMED(3, convert_store(item, d0));
       if (two) F16_TIMED(4, convert_store(item + 1, d1));
     }
-    F16_TRACE_STORE(2, warp == 4 && lane == 0);
+    F16_TRACE_STORE(2, warp == W_PRODUCER0 && lane == 0);
   } else {
     // ================= epilogue ======================================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
     const int q = warp & 3;
-    const int e = tid - (NUM_THREADS - NUM_EPILOGUE);          // 0..127
+    const int e = tid - 32 * W_EPILOGUE0;                      // 0..127
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * q) << 16);
     float* sbias = reinterpret_cast<float*>(base_ptr + L::BIAS);
     const uint32_t stage_u32 = base + L::STAGING + q * L::STG_BLOCKS * 4096;
@@ -468,6 +512,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       auto promote = [&]() {
         const int buf = chunkcount % NBUF;
         F16_WAIT(0, bar_main_full(buf), (chunkcount / NBUF) & 1);
+        if (warp == W_EPILOGUE0 && lane == 0) F16_STAMP(6, chunkcount);
         tc_fence_after();
 #pragma unroll
         for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
@@ -478,6 +523,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         }
         tc_fence_before();
         mbar_arrive(bar_main_empty(buf));
+        if (warp == W_EPILOGUE0 && lane == 0) F16_STAMP(7, chunkcount);
         ++chunkcount;
       };
       for (int c = 0; c < num_chunks - 1; ++c) promote();
@@ -564,14 +610,14 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       }
     }
     tma_store_wait_all();
-    F16_TRACE_STORE(3, warp == 12 && lane == 0);
+    F16_TRACE_STORE(3, warp == W_EPILOGUE0 && lane == 0);
     const float2 ck = unpack_f32x2(chk);
     if ((ck.x != ck.x || ck.y != ck.y) && status != nullptr) atomicOr(status, 1u);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 // OIHW -> [plane hi | plane lo], each [coutp][kpad] halfs, K ordered (slot, kappa) with the in-slot permutation
@@ -697,6 +743,9 @@ bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
 #ifdef B200OV_F16_TRACE
 extern "C" int b200ov_debug_f16_trace(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, f16::g_f16_trace, sizeof(f16::g_f16_trace)) == cudaSuccess ? 0 : 2;
+}
+extern "C" int b200ov_debug_f16_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, f16::g_f16_timeline, sizeof(f16::g_f16_timeline)) == cudaSuccess ? 0 : 2;
 }
 #endif
 

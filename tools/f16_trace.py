@@ -40,3 +40,14 @@ for r, (role, keys) in enumerate(names):
     print('%-14s total %9d clk  (%.0f clk per item)' % (role, total, total / max(1, per_cta * slots)))
     for i, kname in enumerate(keys):
         print('    %-40s %9d clk  %5.1f%%' % (kname, int(t[r, i]), 100.0 * t[r, i] / max(1, total)))
+
+tl = (ctypes.c_longlong * (8 * 128))()
+if hasattr(lib, 'b200ov_debug_f16_timeline') and lib.b200ov_debug_f16_timeline(tl) == 0:
+    T = np.array(tl, dtype=np.int64).reshape(8, 128)
+    t0 = T[0, 0]
+    print('item | loads_issued slot_free published | gate_ready | mma_start mma_end   (cycles since the first load issue; item i uses A slot i%4)')
+    for i in range(16, min(per_cta * slots, 56)):
+        print('%4d | %8d %8d %8d | %8d | %8d %8d' % ((i,) + tuple(int(T[e, i] - t0) for e in range(6))))
+    print('chunk | epilogue_got epilogue_released')
+    for c in range(4, 14):
+        print('%4d | %8d %8d' % (c, int(T[6, c] - t0), int(T[7, c] - t0)))
