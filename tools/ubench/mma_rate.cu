@@ -1,0 +1,84 @@
+// Micro-benchmark: tcgen05.mma kind::f16 M=128 N=128 K=16 issue/execute rate, one CTA per SM, one issuing thread.
+// mode 0: A in shared memory (SS), one accumulator   mode 1: A in TMEM (TS), one accumulator
+// mode 2: TS, three accumulators in the order main, cross, cross (what conv_f16x2_kernel issues)
+// mode 3: TS, N = 256 per MMA, one accumulator
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../pyopenvino_b200/csrc/tc_ptx.cuh"
+using namespace b200ov::ptx;
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5;
+  // zero the operand tiles (A: 128 rows x 128 B, B: 256 rows x 128 B)
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  if (warp == 1 && elect_one_sync()) {
+    const uint64_t a_desc = make_smem_desc_sw128(base), b_desc = make_smem_desc_sw128(base + 16384);
+    const int n = mode == 3 ? 256 : 128;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) umma_f16_ss(tmem, a_desc, b_desc, idesc, 1u);
+      } else if (mode == 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
+      } else if (mode == 2) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_f16_ts(tmem, tmem + 384 + 8 * k, b_desc, idesc, 1u);
+          umma_f16_ts(tmem + 256, tmem + 400 + 8 * k, b_desc, idesc, 1u);
+          umma_f16_ts(tmem + 256, tmem + 384 + 8 * k, b_desc + 2, idesc, 1u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();               // all issued (back-pressured by the queue)
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();               // all executed
+    out[2 * blockIdx.x] = (unsigned long long)(t1 - t0);
+    out[2 * blockIdx.x + 1] = (unsigned long long)(t2 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  unsigned long long* out;
+  cudaMalloc(&out, 148 * 16);
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 2048);
+  const int iters = 2000;
+  const char* names[4] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator"};
+  for (int mode = 0; mode < 4; ++mode) {
+    mma_rate_kernel<<<148, 128, 16384 + 32768 + 2048>>>(mode, iters, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
+    unsigned long long h[2];
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-30s: %7.1f clk per MMA issued, %7.1f clk per MMA executed\n", names[mode], (double)h[0] / (6.0 * iters), (double)h[1] / (6.0 * iters));
+  }
+  return 0;
+}
