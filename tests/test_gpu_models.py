@@ -228,3 +228,51 @@ def test_async_requests_match_sync_infer(model_dir):
     got.append(exe.wait(pending)[out])
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+# ---- BASELINE.json full-size configurations: size-independent properties -------------------------------------------
+
+def test_googlenet_batch256_rows_are_batch1_results(model_dir):
+    """configs[2] at the bench size (256 images per GPU): the batched result is the stack of the batch-1 results
+    (SURVEY.md section 0.4), replay is deterministic, every row is a probability vector, and the rows checked against
+    the oracle engine keep its argmax."""
+    from oracle import ref_engine
+    from tools.synth_bin import synth_input
+    x = synth_input('googlenet-v1', batch=256, seed=31)
+    net, exe = _load(model_dir, 'googlenet-v1', batch=256)
+    name, out = net.inputs[0]['name'], net.outputs[0]['name']
+    full = exe.infer({name: x})[out]
+    assert full.shape == (256, 1000)
+    assert np.array_equal(full, exe.infer({name: x})[out])
+    assert np.all(np.isfinite(full)) and np.all(full >= 0)
+    assert np.allclose(full.sum(axis=1), 1.0, atol=1e-5)
+    net1, exe1 = _load(model_dir, 'googlenet-v1', batch=1)
+    oracle = ref_engine.load(os.path.join(model_dir, 'googlenet-v1.xml'), 'special')
+    for i in (0, 97, 255):
+        one = exe1.infer({net1.inputs[0]['name']: x[i:i + 1]})[net1.outputs[0]['name']]
+        ok, msg = close(full[i:i + 1], one, rtol=1e-5, atol=1e-8)
+        assert ok, (i, msg)
+        want = oracle.infer({name: x[i:i + 1]})[out]
+        ok, msg = close(full[i:i + 1], want, rtol=1e-4, atol=1e-6)
+        assert ok, (i, msg)
+        assert np.argmax(full[i]) == np.argmax(want)
+
+
+def test_ssd_batch64_records_are_batch1_records(model_dir):
+    """configs[3] at the bench size (64 images per GPU): image i's DetectionOutput record block equals the batch-1
+    run on image i -- rank and class id bit for bit, scores and boxes within the FP32 tolerance."""
+    from tools.synth_bin import synth_input
+    x = synth_input('ssd_mobilenet_v1_coco', batch=64, seed=33)
+    net, exe = _load(model_dir, 'ssd_mobilenet_v1_coco', batch=64)
+    name, out = net.inputs[0]['name'], net.outputs[0]['name']
+    full = exe.infer({name: x})[out]
+    keep = full.shape[2] // 64
+    assert np.array_equal(full, exe.infer({name: x})[out])
+    net1, exe1 = _load(model_dir, 'ssd_mobilenet_v1_coco', batch=1)
+    for i in (0, 21, 63):
+        one = exe1.infer({net1.inputs[0]['name']: x[i:i + 1]})[net1.outputs[0]['name']]
+        blk = full[0, 0, i * keep:(i + 1) * keep]
+        ref = one[0, 0, :keep]
+        assert np.array_equal(blk[:, 0:2], ref[:, 0:2]), i          # rank + class id, in order
+        ok, msg = close(blk[:, 2:], ref[:, 2:], rtol=1e-4, atol=1e-5)
+        assert ok, (i, msg)
