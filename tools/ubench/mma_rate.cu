@@ -2,6 +2,8 @@
 // mode 0: A in shared memory (SS), one accumulator   mode 1: A in TMEM (TS), one accumulator
 // mode 2: TS, three accumulators in the order main, cross, cross (what conv_f16x2_kernel issues)
 // mode 3: TS, N = 256 per MMA, one accumulator
+// mode 4: as mode 2 plus one tcgen05.commit (to an mbarrier nobody waits on) after every 6 MMAs
+// mode 5: as mode 2 plus three commits after every 6 MMAs
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,10 +22,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, u
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint32_t tmem_ptr;
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy[4];
   const int warp = threadIdx.x >> 5;
   // zero the operand tiles (A: 128 rows x 128 B, B: 256 rows x 128 B)
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&dummy[i]), 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_ptr), 512);
   fence_proxy_async();
   tc_fence_before();
@@ -42,13 +45,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, u
       } else if (mode == 1) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
-      } else if (mode == 2) {
+      } else if (mode == 2 || mode == 4 || mode == 5) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           umma_f16_ts(tmem, tmem + 384 + 8 * k, b_desc, idesc, 1u);
           umma_f16_ts(tmem + 256, tmem + 400 + 8 * k, b_desc, idesc, 1u);
           umma_f16_ts(tmem + 256, tmem + 384 + 8 * k, b_desc + 2, idesc, 1u);
         }
+        if (mode >= 4) umma_commit(smem_u32(&dummy[0]));
+        if (mode == 5) { umma_commit(smem_u32(&dummy[1])); umma_commit(smem_u32(&dummy[2])); }
       } else {
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
@@ -71,8 +76,8 @@ int main() {
   cudaMalloc(&out, 148 * 16);
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 2048);
   const int iters = 2000;
-  const char* names[4] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator"};
-  for (int mode = 0; mode < 4; ++mode) {
+  const char* names[6] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator", "TS  main/cross/cross + 1 commit/6", "TS  main/cross/cross + 3 commits/6"};
+  for (int mode = 0; mode < 6; ++mode) {
     mma_rate_kernel<<<148, 128, 16384 + 32768 + 2048>>>(mode, iters, out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
