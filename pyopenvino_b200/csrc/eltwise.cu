@@ -181,8 +181,18 @@ int b200ov_affine_act(const float* x, float* y, int64_t rows, int c, int x_ld, i
   B200OV_REQUIRE(x && y && rows >= 0 && c > 0 && x_ld >= c && y_ld >= c, "affine_act: bad argument");
   B200OV_REQUIRE(act >= B200OV_ACT_NONE && act <= B200OV_ACT_SIGMOID, "affine_act: bad activation");
   if (rows == 0) return B200OV_OK;
-  const bool vec = (c % 4 == 0) && (x_ld % 4 == 0) && (y_ld % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t s = as_stream(stream);
+  // no per-channel operand and dense rows: the channel structure does not matter, treat the tensor as one flat row
+  // (e.g. Sigmoid over the SSD class scores, 91 channels: 128-bit accesses instead of scalar ones)
+  if (scale_vec == nullptr && shift_vec == nullptr && x_ld == c && y_ld == c && (rows * c) % 4 == 0 && rows * c < 0x7fffffffLL &&
+      aligned16(x) && aligned16(y) && c % 4 != 0) {
+    const int flat = (int)(rows * c);
+    affine_act_kernel<4><<<bw_grid(flat / 4, 256), 256, 0, s>>>(x, y, 1, flat, flat, flat, has_scale, nullptr, scale_s, has_shift,
+                                                             nullptr, shift_s, act, act_lo, act_hi);
+    B200OV_LAUNCH_CHECK("affine_act_kernel");
+    return B200OV_OK;
+  }
+  const bool vec = (c % 4 == 0) && (x_ld % 4 == 0) && (y_ld % 4 == 0) && aligned16(x) && aligned16(y);
   if (vec)
     affine_act_kernel<4><<<bw_grid(rows * (c / 4), 256), 256, 0, s>>>(x, y, rows, c, x_ld, y_ld, has_scale, scale_vec, scale_s,
                                                                       has_shift, shift_vec, shift_s, act, act_lo, act_hi);
