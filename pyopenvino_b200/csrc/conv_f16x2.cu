@@ -51,13 +51,16 @@ using namespace ptx;
 
 constexpr int BLOCK_M = 128;
 constexpr int SLOT_K = 32;             // K elements per A slot (4 units of 8 channels)
-// TMEM columns: [0, NBUF*N) hi*hi accumulator(s), [NBUF*N, (NBUF+1)*N) cross terms, then the A ring, 32 columns per
-// slot (16 hi + 16 lo), at most 8 slots.
+// TMEM columns: [0, NBUF*N) hi*hi accumulator(s), then NCROSS cross-term accumulators of N columns, then the A ring,
+// 32 columns per slot (16 hi + 16 lo), at most 8 slots.
 #ifndef B200OV_F16_NBUF128
 #define B200OV_F16_NBUF128 2
 #endif
 constexpr int nbuf(int block_n) { return block_n > 64 ? B200OV_F16_NBUF128 : 2; }
-constexpr int a_col0(int block_n) { return (nbuf(block_n) + 1) * block_n; }
+// cross-term accumulators: two (alternating per tile) where TMEM has room, so that the MMA warp starts the next tile
+// while the epilogue still reads the previous one; with 128 columns per buffer there is room for one only
+constexpr int ncross(int block_n) { return block_n <= 64 ? 2 : 1; }
+constexpr int a_col0(int block_n) { return (nbuf(block_n) + ncross(block_n)) * block_n; }
 constexpr int a_slots(int block_n) { return (512 - a_col0(block_n)) / 32 < 8 ? (512 - a_col0(block_n)) / 32 : 8; }
 constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
 #ifndef B200OV_F16_CHUNK
@@ -79,6 +82,7 @@ constexpr int W_TMA = W_EPILOGUE0 + 4, W_MMA = W_TMA + 1, W_GATE = W_TMA + 2;   
 // register budget per warpgroup (setmaxnreg): 40 + 2 * 136 + 200 = 512 = 4 * 128 (the launch allocation)
 constexpr int REGS_CONTROL = 40, REGS_PRODUCER = 136, REGS_EPILOGUE = 200;
 constexpr int EPI_BAR_ID = 1;
+constexpr int ID_A0 = 2;                 // named barriers 2 .. 2 + A_SLOTS - 1: A slot written (producer set + MMA warp)
 constexpr float LO_SCALE = 2048.f;     // 2^11
 constexpr float LO_UNSCALE = 1.f / 2048.f;
 
@@ -130,9 +134,9 @@ struct Smem {
   static constexpr int STAGING_BYTES = 4 * STG_BLOCKS * 4096;
   static constexpr int BIAS = STAGING + STAGING_BYTES;                 // BLOCK_N floats
   static constexpr int BARS = BIAS + BLOCK_N * 4;
-  // b_full[SB], b_empty[SB], a_full[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full, cross_empty
+  // b_full[SB], b_empty[SB], (unused)[A_SLOTS], a_empty[A_SLOTS], main_full[2], main_empty[2], cross_full[2], cross_empty[2]
   static constexpr int A_SLOTS = a_slots(BLOCK_N);
-  static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 6;
+  static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 8;
   static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
   static constexpr int READY = TMEM_PTR + 8;                           // gate warp -> MMA warp: slots whose inputs are ready
   static constexpr int TOTAL = TMEM_PTR + 16 + 1024;                   // + slack for the 1024-byte alignment of the base
@@ -214,17 +218,24 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
   constexpr int A_COL0 = a_col0(BLOCK_N);
   constexpr int NBUF = nbuf(BLOCK_N);
   constexpr int CHUNK = chunk_slots(BLOCK_N);
+  constexpr int NCROSS = ncross(BLOCK_N);
+  constexpr int ID_B0 = ID_A0 + A_SLOTS;   // named barriers of the B stages (gate warp + MMA warp)
+  // With one cross buffer the epilogue's "accumulator drained" signals are on the critical path of every tile
+  // boundary: they go straight to the MMA warp on named barriers (epilogue warps + MMA warp) instead of through
+  // an mbarrier and the gate warp.
+  constexpr bool DIRECT_EMPTY = NCROSS == 1;
+  constexpr int ID_X = ID_B0 + SB, ID_M0 = ID_X + 1;
+  static_assert(ID_B0 + SB + (DIRECT_EMPTY ? 1 + NBUF : 0) <= 16, "out of named barriers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   auto bar_b_full = [&](int s) { return base + L::BARS + 8 * s; };
   auto bar_b_empty = [&](int s) { return base + L::BARS + 8 * (SB + s); };
-  auto bar_a_full = [&](int s) { return base + L::BARS + 8 * (2 * SB + s); };
   auto bar_a_empty = [&](int s) { return base + L::BARS + 8 * (2 * SB + A_SLOTS + s); };
   auto bar_main_full = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + i); };
   auto bar_main_empty = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 2 + i); };
-  const uint32_t bar_cross_full = base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 4);
-  const uint32_t bar_cross_empty = base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 5);
+  auto bar_cross_full = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 4 + i); };
+  auto bar_cross_empty = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 6 + i); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_PTR);
 
   const int tid = threadIdx.x;
@@ -236,15 +247,16 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       mbar_init(bar_b_empty(s), 1);
     }
     for (int s = 0; s < A_SLOTS; ++s) {
-      mbar_init(bar_a_full(s), SET_THREADS);
       mbar_init(bar_a_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_main_full(i), 1);
       mbar_init(bar_main_empty(i), NUM_EPILOGUE);
     }
-    mbar_init(bar_cross_full, 1);
-    mbar_init(bar_cross_empty, NUM_EPILOGUE);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_cross_full(i), 1);
+      mbar_init(bar_cross_empty(i), NUM_EPILOGUE);
+    }
     *reinterpret_cast<volatile uint32_t*>(base_ptr + L::READY) = 0u;
     fence_mbar_init();
     prefetch_tensormap(&map_hi);
@@ -287,74 +299,71 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     } else if (warp == W_MMA) {
       // ================= MMA issuer ==================================================================
       constexpr uint32_t idesc = instr_desc(BLOCK_N);
-      const uint32_t tmem_cross = tmem_base + NBUF * BLOCK_N;
       F16_TRACE_DECL
-      // One elected lane runs the whole loop.  The issue of a UTCHMMA blocks while the tensor-pipe queue is full, so
-      // everything else this thread does per slot (addresses of the next slot, its ready poll) is placed BETWEEN the two
-      // K steps of the current slot, when the queue is fullest, and the descriptors are derived from two values built once.
-      if (elect_one_sync()) {
-        const uint64_t desc_hi0 = make_smem_desc_sw128(base + L::B_HI), desc_lo0 = make_smem_desc_sw128(base + L::B_LO);
-        struct Slot {
-          uint32_t a_hi, tmem_main, acc_main, acc_cross, bar_a, bar_b, bar_main;
-          uint64_t b_hi, b_lo;
-          bool commit_b, commit_main, commit_cross;
-        };
-        int tl = 0, slot = 0;
-        uint32_t acount = 0, bcount = 0, chunkcount = 0;
-        const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
-        auto prep = [&](Slot& o) {                   // describe item (tl, slot), then advance the counters
+      // The whole warp runs the loop with warp-uniform bookkeeping (ring positions advance by increments, no division),
+      // and one elected lane issues.  What this thread executes per slot is the critical path of the kernel: six MMAs
+      // are 384 tensor-pipe cycles, and an earlier version of this loop (per-slot descriptor structs built in a
+      // divergent single-lane branch, ~50 dependent ALU ops + R2UR moves + a spilled local) needed ~700 cycles per
+      // slot, so the pipe idled half of the time (tools/f16_trace.py).
+      const uint64_t desc_hi0 = make_smem_desc_sw128(base + L::B_HI), desc_lo0 = make_smem_desc_sw128(base + L::B_LO);
+      constexpr uint32_t STAGE_DESC = (uint32_t)(L::B_PLANE_BYTES >> 4);
+      static_assert((A_SLOTS & (A_SLOTS - 1)) == 0, "A ring size must be a power of two");
+      uint32_t as = 0, bs = 0, buf = 0, ready = 0, chunks = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        uint32_t in_chunk = 0;
+        const int xb = NCROSS == 2 ? (tl & 1) : 0;
+        const uint32_t tmem_cross = tmem_base + (NBUF + xb) * BLOCK_N;
+        for (int slot = 0; slot < p.num_slots; ++slot) {
           const bool last = slot == p.num_slots - 1;
-          const int buf = chunkcount % NBUF, bs = bcount % SB, as = acount % A_SLOTS;
-          const uint64_t off = (uint64_t)((bs * L::B_PLANE_BYTES + (slot & 1) * 64) >> 4);   // stage + second slot of the stage (+64 B along K)
-          o.a_hi = tmem_base + A_COL0 + as * 32;
-          o.tmem_main = tmem_base + buf * BLOCK_N;
-          o.acc_main = slot % CHUNK > 0 ? 1u : 0u;
-          o.acc_cross = slot > 0 ? 1u : 0u;
-          o.b_hi = desc_hi0 + off;
-          o.b_lo = desc_lo0 + off;
-          o.bar_a = bar_a_empty(as); o.bar_b = bar_b_empty(bs); o.bar_main = bar_main_full(buf);
-          o.commit_b = (slot & 1) || last;
-          o.commit_main = slot % CHUNK == CHUNK - 1 || last;
-          o.commit_cross = last;
-          ++acount;
-          if (o.commit_b) ++bcount;
-          if (o.commit_main) ++chunkcount;
-          if (last) { slot = 0; ++tl; } else { ++slot; }
-        };
-        Slot cur, nxt;
-        if (total_items > 0) {
-          prep(cur);
-          F16_TIMED(3, wait_ready(base + L::READY, 1));
+          const bool odd = (slot & 1) != 0;
+          const bool end_b = odd || last;
+          const bool end_chunk = in_chunk == CHUNK - 1 || last;
+          ++ready;
+          // Waits of this warp are NAMED BARRIERS, not mbarriers or shared-memory flags: every shared-memory operation
+          // of this warp queues behind the producers' gathers in the SM's memory pipe and took 200-300 cycles
+          // (tools/f16_trace.py), more than the six MMAs of a slot take to issue.  The gate warp turns "B stage landed,
+          // accumulators drained" into an arrival on the stage's barrier; the producers arrive on the A slot's barrier.
+          // Reuse of a barrier id is safe: nobody can arrive for the next round of a slot / stage before this warp's
+          // commit for the current round, which follows its bar.sync.
+          if (!odd) F16_TIMED(2, named_bar_sync(ID_B0 + bs, 64));
+          if constexpr (DIRECT_EMPTY) {
+            if (in_chunk == 0 && chunks >= (uint32_t)NBUF) F16_TIMED(0, named_bar_sync(ID_M0 + buf, NUM_EPILOGUE + 32));   // promotion of chunk - NBUF done
+            if (slot == 0 && tl > 0) F16_TIMED(1, named_bar_sync(ID_X, NUM_EPILOGUE + 32));                              // previous tile's cross terms read
+          }
+          F16_TIMED(3, named_bar_sync(ID_A0 + as, SET_THREADS + 32));
           tc_fence_after();
-        }
-        for (uint32_t it = 0; it < total_items; ++it) {
 #ifdef B200OV_F16_TRACE
           const long long t_issue0_ = clock64();
-          F16_STAMP(4, it);
+          if (lane == 0) F16_STAMP(4, ready - 1);
 #endif
-          umma_f16_ts(cur.tmem_main, cur.a_hi, cur.b_hi, idesc, cur.acc_main);
-          umma_f16_ts(tmem_cross, cur.a_hi + 16, cur.b_hi, idesc, cur.acc_cross);
-          umma_f16_ts(tmem_cross, cur.a_hi, cur.b_lo, idesc, 1u);
-          const bool more = it + 1 < total_items;
-          if (more) prep(nxt);
-          umma_f16_ts(cur.tmem_main, cur.a_hi + 8, cur.b_hi + 2, idesc, 1u);
-          umma_f16_ts(tmem_cross, cur.a_hi + 24, cur.b_hi + 2, idesc, 1u);
-          umma_f16_ts(tmem_cross, cur.a_hi + 8, cur.b_lo + 2, idesc, 1u);
-          umma_commit(cur.bar_a);
-          if (cur.commit_b) umma_commit(cur.bar_b);
-          if (cur.commit_main) umma_commit(cur.bar_main);
-          if (cur.commit_cross) umma_commit(bar_cross_full);
+          const uint32_t a_hi = tmem_base + A_COL0 + as * 32;
+          const uint32_t d_main = tmem_base + buf * BLOCK_N;
+          const uint64_t b_hi = desc_hi0 + (uint64_t)(bs * STAGE_DESC + (odd ? 4u : 0u));     // second slot of a stage: +64 B along K
+          const uint64_t b_lo = desc_lo0 + (uint64_t)(bs * STAGE_DESC + (odd ? 4u : 0u));
+          if (elect_one_sync()) {
+            umma_f16_ts(d_main, a_hi, b_hi, idesc, in_chunk > 0 ? 1u : 0u);
+#ifndef B200OV_F16_EXP_ONEMMA
+            umma_f16_ts(tmem_cross, a_hi + 16, b_hi, idesc, slot > 0 ? 1u : 0u);
+            umma_f16_ts(tmem_cross, a_hi, b_lo, idesc, 1u);
+#endif
+            umma_f16_ts(d_main, a_hi + 8, b_hi + 2, idesc, 1u);
+#ifndef B200OV_F16_EXP_ONEMMA
+            umma_f16_ts(tmem_cross, a_hi + 24, b_hi + 2, idesc, 1u);
+            umma_f16_ts(tmem_cross, a_hi + 8, b_lo + 2, idesc, 1u);
+#endif
+            umma_commit(bar_a_empty(as));
+            if (end_b) umma_commit(bar_b_empty(bs));
+            if (end_chunk) umma_commit(bar_main_full(buf));
+            if (last) umma_commit(bar_cross_full(xb));
+          }
+          __syncwarp();
 #ifdef B200OV_F16_TRACE
           tr_[5] += clock64() - t_issue0_;
-          F16_STAMP(5, it);
+          if (lane == 0) F16_STAMP(5, ready - 1);
 #endif
-          if (more) {
-            // all inputs of the next slot (accumulators drained, B stage landed, A slot written) were awaited by the
-            // gate warp; its shared-memory counter costs one short load here instead of four mbarrier try_waits
-            F16_TIMED(3, wait_ready(base + L::READY, it + 2));
-            tc_fence_after();
-            cur = nxt;
-          }
+          as = (as + 1) & (A_SLOTS - 1);
+          if (end_b) bs = bs + 1 == SB ? 0 : bs + 1;
+          if (end_chunk) { buf = buf + 1 == NBUF ? 0 : buf + 1; in_chunk = 0; ++chunks; } else { ++in_chunk; }
         }
       }
       __syncwarp();
@@ -363,19 +372,22 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       // ================= gate ========================================================================
       // Runs the MMA warp's waits ahead of it: the UTCHMMA issue blocks while the tensor-pipe queue is full,
       // and four serial mbarrier waits per slot in the issuing thread left the pipe idle half of the time.
-      uint32_t acount = 0, bcount = 0, chunkcount = 0;
+      static_assert(CHUNK % 2 == 0, "a B stage (two slots) must not straddle promotion chunks");
+      uint32_t bcount = 0, chunkcount = 0;
       for (int tl = 0; tl < my_tiles; ++tl) {
-        for (int slot = 0; slot < p.num_slots; ++slot) {
-          const bool last = slot == p.num_slots - 1;
-          if (slot % CHUNK == 0) mbar_wait(bar_main_empty(chunkcount % NBUF), ((chunkcount / NBUF) & 1) ^ 1);   // promotion of chunk-NBUF done
-          if (slot == 0) mbar_wait(bar_cross_empty, (tl & 1) ^ 1);                                    // previous tile's cross terms read
-          if ((slot & 1) == 0) mbar_wait(bar_b_full(bcount % SB), (bcount / SB) & 1);
-          mbar_wait(bar_a_full(acount % A_SLOTS), (acount / A_SLOTS) & 1);
-          ++acount;
-          if ((slot & 1) || last) ++bcount;
-          if (slot % CHUNK == CHUNK - 1 || last) ++chunkcount;
-          if (lane == 0) { st_release_shared(base + L::READY, acount); F16_STAMP(3, acount - 1); }
+        for (int slot = 0; slot < p.num_slots; slot += 2) {          // one B stage = two slots
+          const bool last = slot + 2 >= p.num_slots;
+          const uint32_t bs = bcount % SB;
+          mbar_wait(bar_b_full(bs), (bcount / SB) & 1);
+          if constexpr (!DIRECT_EMPTY) {
+            if (slot % CHUNK == 0) mbar_wait(bar_main_empty(chunkcount % NBUF), ((chunkcount / NBUF) & 1) ^ 1);   // promotion of chunk-NBUF done
+            if (slot == 0) mbar_wait(bar_cross_empty(tl & 1), ((tl >> 1) & 1) ^ 1);                      // cross terms of tile - 2 read
+          }
           __syncwarp();
+          named_bar_arrive(ID_B0 + bs, 64);
+          if (lane == 0) F16_STAMP(3, (uint32_t)(tl * p.num_slots + slot));
+          ++bcount;
+          if ((slot + 2) % CHUNK == 0 || last) ++chunkcount;
         }
       }
     }
@@ -466,7 +478,8 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       }
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
-      mbar_arrive(bar_a_full(as));
+      __syncwarp();
+      named_bar_arrive(ID_A0 + as, SET_THREADS + 32);
       if (q == 0 && lane == 0) F16_STAMP(2, item);
     };
     Run8 d0[4], d1[4];
@@ -522,25 +535,28 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           for (int j = 0; j < 16; ++j) acc[qb * 16 + j] = add2(acc[qb * 16 + j], pack_u32x2(v[2 * j], v[2 * j + 1]));
         }
         tc_fence_before();
-        mbar_arrive(bar_main_empty(buf));
+        if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_M0 + buf, NUM_EPILOGUE + 32); }
+        else mbar_arrive(bar_main_empty(buf));
         if (warp == W_EPILOGUE0 && lane == 0) F16_STAMP(7, chunkcount);
         ++chunkcount;
       };
       for (int c = 0; c < num_chunks - 1; ++c) promote();
       // The cross terms are complete together with the last chunk: read them first so the MMA warp can start
       // the next tile's cross accumulation while the last chunk is still being promoted.
-      F16_WAIT(1, bar_cross_full, tl & 1);
+      const int xb = NCROSS == 2 ? (tl & 1) : 0;
+      F16_WAIT(1, bar_cross_full(xb), NCROSS == 2 ? (tl >> 1) & 1 : tl & 1);
       tc_fence_after();
       const f32x2 unscale = pack_f32x2(LO_UNSCALE, LO_UNSCALE);
 #pragma unroll
       for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_lane + NBUF * BLOCK_N + qb * 32, v);
+        tmem_ld_32x32b_x32(tmem_lane + (NBUF + xb) * BLOCK_N + qb * 32, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[qb * 16 + j] = fma2(pack_u32x2(v[2 * j], v[2 * j + 1]), unscale, acc[qb * 16 + j]);
       }
       tc_fence_before();
-      mbar_arrive(bar_cross_empty);
+      if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_X, NUM_EPILOGUE + 32); }
+      else mbar_arrive(bar_cross_empty(xb));
       promote();
       // activation (None / ReLU / Clamp as one clamp with infinite bounds), staged in shared memory in the
       // 128B-swizzled box layout TMA expects, STG_BLOCKS 32-column blocks per round.  chk turns NaN as soon

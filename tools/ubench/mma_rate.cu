@@ -4,6 +4,10 @@
 // mode 3: TS, N = 256 per MMA, one accumulator
 // mode 4: as mode 2 plus one tcgen05.commit (to an mbarrier nobody waits on) after every 6 MMAs
 // mode 5: as mode 2 plus three commits after every 6 MMAs
+// mode 6: TS, N = 64, one accumulator                  mode 7: TS, N = 64, main/cross/cross + 1 commit/6
+// mode 8 / 9: N = 128 / 64, bursts of 6 MMAs + commit into an IDLE pipe (wait for the commit after every burst):
+//             column 1 = clk to issue one burst, column 2 = clk per burst including its completion
+// mode 10: as mode 4, plus a volatile shared-memory load after the commits of every slot (the ready-flag poll)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,17 +39,32 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, u
   const uint32_t tmem = tmem_ptr;
   if (warp == 1 && elect_one_sync()) {
     const uint64_t a_desc = make_smem_desc_sw128(base), b_desc = make_smem_desc_sw128(base + 16384);
-    const int n = mode == 3 ? 256 : 128;
+    const int n = mode == 3 ? 256 : (mode == 6 || mode == 7 || mode == 9) ? 64 : 128;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
     const long long t0 = clock64();
+    long long issue_clk = 0;
+    uint32_t sink = 0;
     for (int it = 0; it < iters; ++it) {
+      if (mode == 8 || mode == 9) {
+        const long long a0 = clock64();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_f16_ts(tmem, tmem + 384 + 8 * k, b_desc, idesc, 1u);
+          umma_f16_ts(tmem + 256, tmem + 400 + 8 * k, b_desc, idesc, 1u);
+          umma_f16_ts(tmem + 256, tmem + 384 + 8 * k, b_desc + 2, idesc, 1u);
+        }
+        umma_commit(smem_u32(&dummy[0]));
+        issue_clk += clock64() - a0;
+        mbar_wait(smem_u32(&dummy[0]), it & 1);
+        continue;
+      }
       if (mode == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_f16_ss(tmem, a_desc, b_desc, idesc, 1u);
       } else if (mode == 1) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
-      } else if (mode == 2 || mode == 4 || mode == 5) {
+      } else if (mode == 2 || mode == 4 || mode == 5 || mode == 7 || mode == 10) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           umma_f16_ts(tmem, tmem + 384 + 8 * k, b_desc, idesc, 1u);
@@ -53,13 +72,16 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, u
           umma_f16_ts(tmem + 256, tmem + 384 + 8 * k, b_desc + 2, idesc, 1u);
         }
         if (mode >= 4) umma_commit(smem_u32(&dummy[0]));
+        if (mode == 10) sink += ld_volatile_shared(smem_u32(&tmem_ptr));
         if (mode == 5) { umma_commit(smem_u32(&dummy[1])); umma_commit(smem_u32(&dummy[2])); }
       } else {
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
       }
     }
-    const long long t1 = clock64();               // all issued (back-pressured by the queue)
+    long long t1 = clock64();               // all issued (back-pressured by the queue)
+    if (mode == 8 || mode == 9) t1 = t0 + issue_clk * 6;
+    if (sink == 0x12345678u) out[999] = sink;
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
     const long long t2 = clock64();               // all executed
@@ -76,14 +98,16 @@ int main() {
   cudaMalloc(&out, 148 * 16);
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 2048);
   const int iters = 2000;
-  const char* names[6] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator", "TS  main/cross/cross + 1 commit/6", "TS  main/cross/cross + 3 commits/6"};
-  for (int mode = 0; mode < 6; ++mode) {
+  const char* names[11] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator", "TS  main/cross/cross + 1 commit/6", "TS  main/cross/cross + 3 commits/6",
+                           "TS  N=64, one accumulator", "TS  N=64 main/cross/cross + 1 commit/6", "N=128 burst of 6 into idle pipe (x6)", "N=64 burst of 6 into idle pipe (x6)",
+                           "TS  m/c/c + commit + shared load"};
+  for (int mode = 0; mode < 11; ++mode) {
     mma_rate_kernel<<<148, 128, 16384 + 32768 + 2048>>>(mode, iters, out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
     unsigned long long h[2];
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("%-30s: %7.1f clk per MMA issued, %7.1f clk per MMA executed\n", names[mode], (double)h[0] / (6.0 * iters), (double)h[1] / (6.0 * iters));
+    printf("%-40s: %7.1f clk per MMA issued, %7.1f clk per MMA executed\n", names[mode], (double)h[0] / (6.0 * iters), (double)h[1] / (6.0 * iters));
   }
   return 0;
 }
