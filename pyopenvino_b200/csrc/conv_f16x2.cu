@@ -196,6 +196,10 @@ struct Run8 {
 };
 __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
   Run8 r;
+#ifdef B200OV_F16_EXP_NOLOAD
+  for (int i = 0; i < 8; ++i) r.v[i] = __int_as_float(((int)(size_t)p & 0xffff) + 0x3f800000 + i);
+  return r;
+#endif
   if (wide) {
     asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
@@ -308,62 +312,96 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       const uint64_t desc_hi0 = make_smem_desc_sw128(base + L::B_HI), desc_lo0 = make_smem_desc_sw128(base + L::B_LO);
       constexpr uint32_t STAGE_DESC = (uint32_t)(L::B_PLANE_BYTES >> 4);
       static_assert((A_SLOTS & (A_SLOTS - 1)) == 0, "A ring size must be a power of two");
+      // One iteration = one B stage = two slots = 12 MMAs (768 tensor-pipe cycles).  The pipe runs only ~2 MMAs ahead of
+      // the issuing thread (tools/ubench/mma_rate.cu: 190 cycles of other work between bursts of 6 cost 78), so what the
+      // thread does between two bursts -- barrier waits, descriptor arithmetic, R2UR moves, commits -- is mostly exposed;
+      // per pair it is paid once instead of twice.
+      // The CTA allocates all 512 TMEM columns, so the allocation starts at lane 0, column 0: with the base a
+      // compile-time constant every TMEM address of this loop is warp-uniform arithmetic (no vector -> uniform moves).
+      if (tmem_base != 0) __trap();
+      constexpr uint32_t tmem_base = 0;
       uint32_t as = 0, bs = 0, buf = 0, ready = 0, chunks = 0;
+#ifdef B200OV_F16_TRACE
+      long long t_prev_end_ = 0;
+#endif
       for (int tl = 0; tl < my_tiles; ++tl) {
         uint32_t in_chunk = 0;
         const int xb = NCROSS == 2 ? (tl & 1) : 0;
         const uint32_t tmem_cross = tmem_base + (NBUF + xb) * BLOCK_N;
-        for (int slot = 0; slot < p.num_slots; ++slot) {
-          const bool last = slot == p.num_slots - 1;
-          const bool odd = (slot & 1) != 0;
-          const bool end_b = odd || last;
-          const bool end_chunk = in_chunk == CHUNK - 1 || last;
-          ++ready;
+        for (int slot = 0; slot < p.num_slots; slot += 2) {
+          const bool two = slot + 1 < p.num_slots;
+          const bool last = slot + 2 >= p.num_slots;
+          const bool end_chunk = in_chunk == CHUNK - 2 || last;
+          const uint32_t as1 = (as + 1) & (A_SLOTS - 1);
           // Waits of this warp are NAMED BARRIERS, not mbarriers or shared-memory flags: every shared-memory operation
           // of this warp queues behind the producers' gathers in the SM's memory pipe and took 200-300 cycles
           // (tools/f16_trace.py), more than the six MMAs of a slot take to issue.  The gate warp turns "B stage landed,
           // accumulators drained" into an arrival on the stage's barrier; the producers arrive on the A slot's barrier.
           // Reuse of a barrier id is safe: nobody can arrive for the next round of a slot / stage before this warp's
           // commit for the current round, which follows its bar.sync.
-          if (!odd) F16_TIMED(2, named_bar_sync(ID_B0 + bs, 64));
+          F16_TIMED(2, named_bar_sync(ID_B0 + bs, 64));
           if constexpr (DIRECT_EMPTY) {
             if (in_chunk == 0 && chunks >= (uint32_t)NBUF) F16_TIMED(0, named_bar_sync(ID_M0 + buf, NUM_EPILOGUE + 32));   // promotion of chunk - NBUF done
-            if (slot == 0 && tl > 0) F16_TIMED(1, named_bar_sync(ID_X, NUM_EPILOGUE + 32));                              // previous tile's cross terms read
+            if (slot == 0 && tl > 0) F16_TIMED(0, named_bar_sync(ID_X, NUM_EPILOGUE + 32));                              // previous tile's cross terms read
           }
           F16_TIMED(3, named_bar_sync(ID_A0 + as, SET_THREADS + 32));
+          if (two) F16_TIMED(3, named_bar_sync(ID_A0 + as1, SET_THREADS + 32));
+#ifdef B200OV_F16_TRACE
+          const long long t_f0_ = clock64();
+          if (t_prev_end_ != 0) tr_[6] += t_f0_ - t_prev_end_;       // whole gap since the previous burst
+#endif
           tc_fence_after();
 #ifdef B200OV_F16_TRACE
           const long long t_issue0_ = clock64();
-          if (lane == 0) F16_STAMP(4, ready - 1);
+          tr_[4] += t_issue0_ - t_f0_;
+          if (lane == 0) { F16_STAMP(4, ready); F16_STAMP(4, ready + 1); }
 #endif
-          const uint32_t a_hi = tmem_base + A_COL0 + as * 32;
+          const uint32_t a0 = tmem_base + A_COL0 + as * 32, a1 = tmem_base + A_COL0 + as1 * 32;
           const uint32_t d_main = tmem_base + buf * BLOCK_N;
-          const uint64_t b_hi = desc_hi0 + (uint64_t)(bs * STAGE_DESC + (odd ? 4u : 0u));     // second slot of a stage: +64 B along K
-          const uint64_t b_lo = desc_lo0 + (uint64_t)(bs * STAGE_DESC + (odd ? 4u : 0u));
+          const uint64_t b_hi = desc_hi0 + (uint64_t)(bs * STAGE_DESC);
+          const uint64_t b_lo = desc_lo0 + (uint64_t)(bs * STAGE_DESC);
           if (elect_one_sync()) {
-            umma_f16_ts(d_main, a_hi, b_hi, idesc, in_chunk > 0 ? 1u : 0u);
-#ifndef B200OV_F16_EXP_ONEMMA
-            umma_f16_ts(tmem_cross, a_hi + 16, b_hi, idesc, slot > 0 ? 1u : 0u);
-            umma_f16_ts(tmem_cross, a_hi, b_lo, idesc, 1u);
+#ifdef B200OV_F16_TRACE
+            tr_[1] += clock64() - t_issue0_;                          // descriptors + election, before the first MMA
 #endif
-            umma_f16_ts(d_main, a_hi + 8, b_hi + 2, idesc, 1u);
+            umma_f16_ts(d_main, a0, b_hi, idesc, in_chunk > 0 ? 1u : 0u);
 #ifndef B200OV_F16_EXP_ONEMMA
-            umma_f16_ts(tmem_cross, a_hi + 24, b_hi + 2, idesc, 1u);
-            umma_f16_ts(tmem_cross, a_hi + 8, b_lo + 2, idesc, 1u);
+            umma_f16_ts(tmem_cross, a0 + 16, b_hi, idesc, slot > 0 ? 1u : 0u);
+            umma_f16_ts(tmem_cross, a0, b_lo, idesc, 1u);
+#endif
+            umma_f16_ts(d_main, a0 + 8, b_hi + 2, idesc, 1u);
+#ifndef B200OV_F16_EXP_ONEMMA
+            umma_f16_ts(tmem_cross, a0 + 24, b_hi + 2, idesc, 1u);
+            umma_f16_ts(tmem_cross, a0 + 8, b_lo + 2, idesc, 1u);
 #endif
             umma_commit(bar_a_empty(as));
-            if (end_b) umma_commit(bar_b_empty(bs));
+            if (two) {                               // second slot of the stage: +64 B along K
+              umma_f16_ts(d_main, a1, b_hi + 4, idesc, 1u);
+#ifndef B200OV_F16_EXP_ONEMMA
+              umma_f16_ts(tmem_cross, a1 + 16, b_hi + 4, idesc, 1u);
+              umma_f16_ts(tmem_cross, a1, b_lo + 4, idesc, 1u);
+#endif
+              umma_f16_ts(d_main, a1 + 8, b_hi + 6, idesc, 1u);
+#ifndef B200OV_F16_EXP_ONEMMA
+              umma_f16_ts(tmem_cross, a1 + 24, b_hi + 6, idesc, 1u);
+              umma_f16_ts(tmem_cross, a1 + 8, b_lo + 6, idesc, 1u);
+#endif
+              umma_commit(bar_a_empty(as1));
+            }
+            umma_commit(bar_b_empty(bs));
             if (end_chunk) umma_commit(bar_main_full(buf));
             if (last) umma_commit(bar_cross_full(xb));
           }
           __syncwarp();
 #ifdef B200OV_F16_TRACE
-          tr_[5] += clock64() - t_issue0_;
-          if (lane == 0) F16_STAMP(5, ready - 1);
+          t_prev_end_ = clock64();
+          tr_[5] += t_prev_end_ - t_issue0_;
+          if (lane == 0) { F16_STAMP(5, ready); F16_STAMP(5, ready + 1); }
 #endif
-          as = (as + 1) & (A_SLOTS - 1);
-          if (end_b) bs = bs + 1 == SB ? 0 : bs + 1;
-          if (end_chunk) { buf = buf + 1 == NBUF ? 0 : buf + 1; in_chunk = 0; ++chunks; } else { ++in_chunk; }
+          ready += two ? 2 : 1;
+          as = two ? (as + 2) & (A_SLOTS - 1) : as1;
+          bs = bs + 1 == SB ? 0 : bs + 1;
+          if (end_chunk) { buf = buf + 1 == NBUF ? 0 : buf + 1; in_chunk = 0; ++chunks; } else { in_chunk += 2; }
         }
       }
       __syncwarp();
@@ -799,7 +837,11 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
   p.units = units;
   p.num_slots = ceil_div(units, 4);
-  const int block_n = d->cout > 64 ? 128 : (d->cout > 32 ? 64 : 32);
+  int block_n = d->cout > 64 ? 128 : (d->cout > 32 ? 64 : 32);
+  if (const char* e = getenv("B200OV_F16_FORCE_N")) {                  // developer knob (tile-width experiments)
+    const int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) block_n = v;
+  }
   p.tiles_n = ceil_div(d->cout, block_n);
   const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n;
   if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");

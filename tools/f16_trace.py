@@ -34,7 +34,7 @@ slots = (units + 3) // 4
 tiles = ((B * oh * oh + 127) // 128) * ((cout + 127) // 128 if cout > 64 else 1)
 per_cta = (tiles + 147) // 148
 print('cin %d cout %d k %d hw %d batch %d: %d slots/tile, %d tiles, <= %d tiles per CTA, %d items per CTA' % (cin, cout, k, hw, B, slots, tiles, per_cta, per_cta * slots))
-names = [('B loader', ['wait b_empty']), ('MMA', ['-', '-', 'wait B stage (named barrier)', 'wait A slot (named barrier)', '-', 'descriptors + 6 MMA + commits']),
+names = [('B loader', ['wait b_empty']), ('MMA', ['wait main drained (N=128)', 'descriptors + election before first MMA', 'wait B stage (named barrier)', 'wait A slot (named barrier)', 'tcgen05.fence::after', 'descriptors + MMAs + commits', 'gap between bursts (incl. waits)']),
          ('producer w4', ['wait a_empty', 'issue loads', 'wait tmem st', 'convert+store item0 (incl. waits)', 'convert+store item1 (incl. waits)']),
          ('epilogue w12', ['wait main_full', 'wait cross_full', 'wait tma store read'])]
 for r, (role, keys) in enumerate(names):
