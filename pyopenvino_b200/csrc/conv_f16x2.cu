@@ -243,7 +243,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_PTR);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // broadcast: tells ptxas the role branches are warp-uniform
 
   if (tid == 0) {
     for (int s = 0; s < SB; ++s) {
@@ -319,7 +319,6 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       // The CTA allocates all 512 TMEM columns, so the allocation starts at lane 0, column 0: with the base a
       // compile-time constant every TMEM address of this loop is warp-uniform arithmetic (no vector -> uniform moves).
       if (tmem_base != 0) __trap();
-      constexpr uint32_t tmem_base = 0;
       uint32_t as = 0, bs = 0, buf = 0, ready = 0, chunks = 0;
 #ifdef B200OV_F16_TRACE
       long long t_prev_end_ = 0;
@@ -327,7 +326,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       for (int tl = 0; tl < my_tiles; ++tl) {
         uint32_t in_chunk = 0;
         const int xb = NCROSS == 2 ? (tl & 1) : 0;
-        const uint32_t tmem_cross = tmem_base + (NBUF + xb) * BLOCK_N;
+        const uint32_t tmem_cross = (NBUF + xb) * BLOCK_N;
         for (int slot = 0; slot < p.num_slots; slot += 2) {
           const bool two = slot + 1 < p.num_slots;
           const bool last = slot + 2 >= p.num_slots;
@@ -356,42 +355,15 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           tr_[4] += t_issue0_ - t_f0_;
           if (lane == 0) { F16_STAMP(4, ready); F16_STAMP(4, ready + 1); }
 #endif
-          const uint32_t a0 = tmem_base + A_COL0 + as * 32, a1 = tmem_base + A_COL0 + as1 * 32;
-          const uint32_t d_main = tmem_base + buf * BLOCK_N;
+          const uint32_t a0 = A_COL0 + as * 32, a1 = A_COL0 + as1 * 32;       // TMEM base is 0 (checked above)
+          const uint32_t d_main = buf * BLOCK_N;
           const uint64_t b_hi = desc_hi0 + (uint64_t)(bs * STAGE_DESC);
           const uint64_t b_lo = desc_lo0 + (uint64_t)(bs * STAGE_DESC);
-          if (elect_one_sync()) {
-#ifdef B200OV_F16_TRACE
-            tr_[1] += clock64() - t_issue0_;                          // descriptors + election, before the first MMA
-#endif
-            umma_f16_ts(d_main, a0, b_hi, idesc, in_chunk > 0 ? 1u : 0u);
-#ifndef B200OV_F16_EXP_ONEMMA
-            umma_f16_ts(tmem_cross, a0 + 16, b_hi, idesc, slot > 0 ? 1u : 0u);
-            umma_f16_ts(tmem_cross, a0, b_lo, idesc, 1u);
-#endif
-            umma_f16_ts(d_main, a0 + 8, b_hi + 2, idesc, 1u);
-#ifndef B200OV_F16_EXP_ONEMMA
-            umma_f16_ts(tmem_cross, a0 + 24, b_hi + 2, idesc, 1u);
-            umma_f16_ts(tmem_cross, a0 + 8, b_lo + 2, idesc, 1u);
-#endif
-            umma_commit(bar_a_empty(as));
-            if (two) {                               // second slot of the stage: +64 B along K
-              umma_f16_ts(d_main, a1, b_hi + 4, idesc, 1u);
-#ifndef B200OV_F16_EXP_ONEMMA
-              umma_f16_ts(tmem_cross, a1 + 16, b_hi + 4, idesc, 1u);
-              umma_f16_ts(tmem_cross, a1, b_lo + 4, idesc, 1u);
-#endif
-              umma_f16_ts(d_main, a1 + 8, b_hi + 6, idesc, 1u);
-#ifndef B200OV_F16_EXP_ONEMMA
-              umma_f16_ts(tmem_cross, a1 + 24, b_hi + 6, idesc, 1u);
-              umma_f16_ts(tmem_cross, a1 + 8, b_lo + 6, idesc, 1u);
-#endif
-              umma_commit(bar_a_empty(as1));
-            }
-            umma_commit(bar_b_empty(bs));
-            if (end_chunk) umma_commit(bar_main_full(buf));
-            if (last) umma_commit(bar_cross_full(xb));
-          }
+          umma_f16x2_slot(d_main, tmem_cross, a0, b_hi, b_lo, idesc, in_chunk > 0 ? 1u : 0u, slot > 0 ? 1u : 0u, bar_a_empty(as));
+          if (two) umma_f16x2_slot(d_main, tmem_cross, a1, b_hi + 4, b_lo + 4, idesc, 1u, 1u, bar_a_empty(as1));   // +64 B along K
+          umma_commit_elect(bar_b_empty(bs), 1u);
+          umma_commit_elect(bar_main_full(buf), end_chunk ? 1u : 0u);
+          umma_commit_elect(bar_cross_full(xb), last ? 1u : 0u);
           __syncwarp();
 #ifdef B200OV_F16_TRACE
           t_prev_end_ = clock64();

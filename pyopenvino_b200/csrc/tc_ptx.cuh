@@ -119,6 +119,46 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The six MMAs of one A slot (two K steps of hi*hi, lo*hi, hi*lo) and the commit that releases the slot, issued by one
+// elected lane from CONVERGED code: with the election inside the asm block the surrounding loop stays warp-uniform, and
+// ptxas keeps its state and all operand arithmetic on the uniform datapath.  Wrapped in `if (elect_one_sync())` the
+// same code is a divergent single-lane region: every operand is computed in vector registers and moved with R2UR, and
+// an R2UR into a uniform register that a queued UTCHMMA still has to read stalls on the scoreboard -- 27% of the MMA
+// warp's time in the ncu source view of that version.
+__device__ __forceinline__ void umma_f16x2_slot(uint32_t d_main, uint32_t d_cross, uint32_t a0, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t acc_main, uint32_t acc_cross, uint32_t bar_a_empty) {
+  asm volatile(
+      "{\n\t.reg .pred pm, pc, le;\n\t.reg .b32 a8, a16, a24;\n\t.reg .b64 h2, l2;\n\t"
+      "setp.ne.b32 pm, %6, 0;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "elect.sync _|le, 0xffffffff;\n\t"
+      "add.u32 a8, %2, 8;\n\t"
+      "add.u32 a16, %2, 16;\n\t"
+      "add.u32 a24, %2, 24;\n\t"
+      "add.u64 h2, %3, 2;\n\t"
+      "add.u64 l2, %4, 2;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pm;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [a16], %3, %5, pc;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %4, %5, 1;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%0], [a8], h2, %5, 1;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [a24], h2, %5, 1;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [a8], l2, %5, 1;\n\t"
+      "@le tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}"
+      ::"r"(d_main), "r"(d_cross), "r"(a0), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_main), "r"(acc_cross), "r"(bar_a_empty)
+      : "memory");
+}
+// tcgen05.commit by one elected lane of a converged warp, if `cond` (warp-uniform) is non-zero
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar, uint32_t cond) {
+  asm volatile(
+      "{\n\t.reg .pred le, pc;\n\t"
+      "elect.sync _|le, 0xffffffff;\n\t"
+      "setp.ne.and.b32 pc, %1, 0, le;\n\t"
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}"
+      ::"r"(bar), "r"(cond)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
