@@ -180,14 +180,26 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 }
 
 // (c0, c1) -> packed FP16 hi pair and scaled-residual lo pair:  c = hi + 2^-11 lo  up to 2^-22 |c|.
-// (c - hi) is exact in FP32 and so is its 2^11 scaling, hence fma(c, 2^11, -(2^11 hi)) is exact too.
+// (c - hi) is exact in FP32 and so is its 2^11 scaling, hence fma(hi, -2^11, 2^11 c) is exact too.  The FMA is the
+// mixed-precision one (FHFMA: f16 x f16 + f32 -> f32), which reads hi straight from the packed pair: five instructions
+// per pair (F2FP, FMUL2, 2 FHFMA, F2FP) -- the producers' instruction count is what bounds this kernel.
 __device__ __forceinline__ void split_pair(float c0, float c1, uint32_t& hi, uint32_t& lo) {
+#ifdef B200OV_F16_EXP_NOCONVERT
+  hi = __float_as_uint(c0); lo = __float_as_uint(c1);
+  return;
+#endif
   const __half2 h = __floats2half2_rn(c0, c1);
-  const float2 hf = __half22float2(h);
-  const f32x2 neg = mul2(pack_f32x2(hf.x, hf.y), pack_f32x2(-LO_SCALE, -LO_SCALE));
-  const float2 r = unpack_f32x2(fma2(pack_f32x2(c0, c1), pack_f32x2(LO_SCALE, LO_SCALE), neg));
-  const __half2 l = __floats2half2_rn(r.x, r.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 s = unpack_f32x2(mul2(pack_f32x2(c0, c1), pack_f32x2(LO_SCALE, LO_SCALE)));
+  float r0, r1;
+  asm("{\n\t.reg .b16 h0, h1, m;\n\t"
+      "mov.b32 {h0, h1}, %2;\n\t"
+      "mov.b16 m, 0xE800;\n\t"                       // -2048 as an FP16 number
+      "fma.rn.f32.f16 %0, h0, m, %3;\n\t"
+      "fma.rn.f32.f16 %1, h1, m, %4;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "r"(hi), "f"(s.x), "f"(s.y));
+  const __half2 l = __floats2half2_rn(r0, r1);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
