@@ -59,7 +59,7 @@ constexpr int SLOT_K = 32;             // K elements per A slot (4 units of 8 ch
 constexpr int nbuf(int block_n) { return block_n > 64 ? B200OV_F16_NBUF128 : 2; }
 // cross-term accumulators: two (alternating per tile) where TMEM has room, so that the MMA warp starts the next tile
 // while the epilogue still reads the previous one; with 128 columns per buffer there is room for one only
-constexpr int ncross(int block_n) { return block_n <= 64 ? 2 : 1; }
+constexpr int ncross(int block_n) { return block_n <= 96 ? 2 : 1; }
 constexpr int a_col0(int block_n) { return (nbuf(block_n) + ncross(block_n)) * block_n; }
 constexpr int a_slots(int block_n) { return (512 - a_col0(block_n)) / 32 < 8 ? (512 - a_col0(block_n)) / 32 : 8; }
 constexpr int STAGE_K = 64;            // K elements per B stage (2 slots): one 128-byte swizzle row of halfs
@@ -129,7 +129,7 @@ struct Smem {
   static constexpr int B_PLANE_BYTES = BLOCK_N * 128;                  // one stage of one plane: BLOCK_N rows x 64 halfs
   static constexpr int B_HI = 0;
   static constexpr int B_LO = B_HI + SB * B_PLANE_BYTES;
-  static constexpr int STG_BLOCKS = BLOCK_N >= 64 ? 2 : 1;            // 32-column blocks staged per round
+  static constexpr int STG_BLOCKS = BLOCK_N == 96 ? 3 : (BLOCK_N >= 64 ? 2 : 1);   // 32-column blocks staged per round
   static constexpr int STAGING = B_LO + SB * B_PLANE_BYTES;            // 4 warps x STG_BLOCKS blocks x 4 KB
   static constexpr int STAGING_BYTES = 4 * STG_BLOCKS * 4096;
   static constexpr int BIAS = STAGING + STAGING_BYTES;                 // BLOCK_N floats
@@ -821,10 +821,14 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
   p.units = units;
   p.num_slots = ceil_div(units, 4);
+  // Tile width: 128 columns, or 96 where that needs no more tiles (C_out in (64, 96], (128, 192], (256, 288]): an
+  // N = 96 MMA takes 56 cycles against 64 for N = 128 (tools/ubench/mma_rate.cu), a 96-wide tile leaves TMEM room
+  // for a second cross-term accumulator, and e.g. C_out = 192 is two full tiles instead of one and a half.
   int block_n = d->cout > 64 ? 128 : (d->cout > 32 ? 64 : 32);
+  if (d->cout > 64 && ceil_div(d->cout, 96) == ceil_div(d->cout, 128)) block_n = 96;
   if (const char* e = getenv("B200OV_F16_FORCE_N")) {                  // developer knob (tile-width experiments)
     const int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) block_n = v;
+    if (v == 32 || v == 64 || v == 96 || v == 128) block_n = v;
   }
   p.tiles_n = ceil_div(d->cout, block_n);
   const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n;
@@ -856,6 +860,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
            : p.wide_loads ? f16::launch<N_, SB_, true, false>(p, x, bias, status, mh, ml, my, s) \
                           : f16::launch<N_, SB_, false, false>(p, x, bias, status, mh, ml, my, s))
   if (block_n == 128) return B200OV_F16_LAUNCH(128, 4);
+  if (block_n == 96) return B200OV_F16_LAUNCH(96, 4);
   if (block_n == 64) return B200OV_F16_LAUNCH(64, 6);
   return B200OV_F16_LAUNCH(32, 6);
 #undef B200OV_F16_LAUNCH

@@ -22,10 +22,10 @@ def launches(src, dst):
     rows = list(csv.reader(open(src)))
     hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
     h = rows[hi]
-    kn, mv, mu = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
+    kn, mv, mu, mn = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit'), h.index('Metric Name')
     agg, tot = collections.OrderedDict(), 0.0
     for r in rows[hi + 1:]:
-        if len(r) <= mv:
+        if len(r) <= mv or r[mn] != 'gpu__time_duration.sum':      # the CSV may carry the DRAM byte counters as well
             continue
         v = float(r[mv].replace(',', ''))
         v = v / 1e3 if r[mu] == 'ns' else v * 1e3 if r[mu] == 'ms' else v

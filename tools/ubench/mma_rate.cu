@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(int mode, int iters, u
   }
   if (warp == 1 && elect_one_sync()) {
     const uint64_t a_desc = make_smem_desc_sw128(base), b_desc = make_smem_desc_sw128(base + 16384);
-    const int n = mode == 3 ? 256 : (mode == 6 || mode == 7 || mode == 9) ? 64 : 128;
+    const int n = mode == 3 ? 256 : (mode == 6 || mode == 7 || mode == 9) ? 64 : mode == 14 ? 96 : mode == 15 ? 192 : mode == 16 ? 32 : 128;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
     const long long t0 = clock64();
     long long issue_clk = 0;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(int mode, int iters, u
         if (mode == 5) { umma_commit(smem_u32(&dummy[1])); umma_commit(smem_u32(&dummy[2])); }
       } else {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);
+        for (int k = 0; k < 6; ++k) umma_f16_ts(tmem, tmem + 384, b_desc, idesc, 1u);      // modes 3, 6, 14, 15, 16: one accumulator, N as above
       }
     }
     long long t1 = clock64();               // all issued (back-pressured by the queue)
@@ -173,9 +173,9 @@ int main() {
   cudaMalloc(&out, 1000 * 16);
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 2048);
   const int iters = 2000;
-  const char* names[14] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator", "TS  main/cross/cross + 1 commit/6", "TS  main/cross/cross + 3 commits/6",
+  const char* names[17] = {"SS  N=128, one accumulator", "TS  N=128, one accumulator", "TS  N=128, main/cross/cross", "TS  N=256, one accumulator", "TS  main/cross/cross + 1 commit/6", "TS  main/cross/cross + 3 commits/6",
                            "TS  N=64, one accumulator", "TS  N=64 main/cross/cross + 1 commit/6", "N=128 burst of 6 into idle pipe (x6)", "N=64 burst of 6 into idle pipe (x6)",
-                           "TS  m/c/c + commit + shared load", "m/c/c, commit, ~200 clk ALU chain", "m/c/c, ~200 clk ALU chain, commit", "m/c/c, ~200 clk ALU chain, no commit"};
+                           "TS  m/c/c + commit + shared load", "m/c/c, commit, ~200 clk ALU chain", "m/c/c, ~200 clk ALU chain, commit", "m/c/c, ~200 clk ALU chain, no commit", "TS  N=96, one accumulator", "TS  N=192, one accumulator", "TS  N=32, one accumulator"};
   float* gbuf;
   cudaMalloc(&gbuf, 148 * 65536 * sizeof(float));
   cudaMemset(gbuf, 0, 148 * 65536 * sizeof(float));
@@ -190,7 +190,7 @@ int main() {
     printf("TS m/c/c + commit, 4 warps of %-10s noise: %7.1f clk per MMA executed\n", noise_names[noise], (double)h[1] / (6.0 * iters * 5));
   }
   for (int fill = 0; fill < 2; ++fill)
-  for (int mode = 0; mode < 14; ++mode) {
+  for (int mode = 0; mode < 17; ++mode) {
     if (mode == 0 && fill) printf("---- random operand data ----\n");
     mma_rate_kernel<<<148, 256, 16384 + 32768 + 16384 + 2048>>>(mode, iters * (fill ? 10 : 1), out, fill, 0, gbuf);
     cudaError_t e = cudaDeviceSynchronize();
