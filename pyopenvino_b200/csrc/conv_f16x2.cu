@@ -661,7 +661,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
 // OIHW -> [plane hi | plane lo], each [coutp][kpad] halfs, K ordered (slot, kappa) with the in-slot permutation
 // the A producers use: kappa = 16*b + 4*u + j  <->  unit 4*slot + u, channel 4*b + j of that unit.
 __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int kh,
-                                        int kw, int coutp, int kpad, int upt, int units, int pair4) {
+                                        int kw, int coutp, int kpad, int upt, int units, int pair4, int kx0) {
   const long long plane = (long long)coutp * kpad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < plane;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -672,9 +672,9 @@ __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __r
     const int cj = ((kappa >> 4) << 2) + (kappa & 3);
     float v = 0.f;
     if (n < cout && unit < units) {
-      if (pair4) {                       // unit = (filter row ky, tap pair kxp): taps 2*kxp, 2*kxp + 1, 4 channels each
-        const int ky = unit / upt, kx = 2 * (unit - ky * upt) + (cj >> 2), c = cj & 3;
-        if (kx < kw && c < cin) v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+      if (pair4) {                       // unit = (filter row ky, tap pair kxp): taps kx0 + 2*kxp, kx0 + 2*kxp + 1, 4 channels each
+        const int ky = unit / upt, kx = kx0 + 2 * (unit - ky * upt) + (cj >> 2), c = cj & 3;
+        if (kx >= 0 && kx < kw && c < cin) v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
       } else {
         const int tap = unit / upt, c = (unit - tap * upt) * 8 + cj;
         if (c < cin) {
@@ -742,11 +742,12 @@ __device__ unsigned int g_status_word;     // sticky: bit 0 = a non-finite value
 
 }  // namespace f16
 
-// cin <= 4: "pair" layout (a unit = two adjacent taps of one filter row x 4 channels; upt = units per filter row);
+// cin <= 4: "pair" layout (a unit = two adjacent taps of one filter row x 4 channels; upt = units per filter row),
+// stored twice: pairs starting at tap 0 and pairs starting at tap -1 (a zero tap), see conv2d_f16x2_multi;
 // otherwise a unit = 8 channels of one tap (upt = units per tap).
 void f16_weight_dims(int cout, int cin, int kh, int kw, int* coutp, int* kpad, int* upt, int* units) {
   const bool pair4 = cin <= 4;
-  const int u = pair4 ? ceil_div(kw, 2) : ceil_div(cin, 8);
+  const int u = pair4 ? ceil_div(kw + 1, 2) : ceil_div(cin, 8);
   const int n_units = pair4 ? kh * u : kh * kw * u;
   if (coutp) *coutp = round_up(cout, 8);
   if (kpad) *kpad = round_up(n_units, 8) * 8;         // whole B stages of 64 K-elements
@@ -757,7 +758,7 @@ void f16_weight_dims(int cout, int cin, int kh, int kw, int* coutp, int* kpad, i
 long long f16_section_floats(int cout, int cin, int kh, int kw) {
   int coutp, kpad;
   f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, nullptr, nullptr);
-  return (long long)coutp * kpad;                     // two planes of halfs
+  return (long long)coutp * kpad * (cin <= 4 ? 2 : 1);   // two planes of halfs (x two tap alignments for the pair layout)
 }
 
 int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s) {
@@ -765,8 +766,13 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
   f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, &upt, &units);
   f16::pack_f16_weights_kernel<<<bw_grid((long long)coutp * kpad, 256), 256, 0, s>>>(w_oihw, reinterpret_cast<__half*>(out), cout,
                                                                                     cin, kh, kw, coutp, kpad, upt, units,
-                                                                                    cin <= 4 ? 1 : 0);
+                                                                                    cin <= 4 ? 1 : 0, 0);
   B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
+  if (cin <= 4) {
+    f16::pack_f16_weights_kernel<<<bw_grid((long long)coutp * kpad, 256), 256, 0, s>>>(
+        w_oihw, reinterpret_cast<__half*>(out) + 2LL * coutp * kpad, cout, cin, kh, kw, coutp, kpad, upt, units, 1, -1);
+    B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
+  }
   return B200OV_OK;
 }
 
@@ -836,10 +842,23 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
   p.pair4 = d->cin <= 4;
-  p.wide_loads = !p.pair4 && (d->x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
-  p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(d->kw);
-  p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
   const __half* hi_plane = reinterpret_cast<const __half*>(wt);
+  int kw_eff = d->kw;
+  if (p.pair4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0) {
+    // Stem with an even horizontal stride on an even-width image (pixel pitch 4 floats): two adjacent pixels are one
+    // 32-byte aligned "super-pixel" of 8 channels, and with the tap pairs aligned to even pixel columns (pairs start at
+    // tap -(pl & 1); the packed weights hold both alignments) the stem is an ordinary 8-channel convolution over the
+    // [h][w/2][8] view: kernel kh x upt, horizontal stride sw/2, left padding ceil(pl/2).  The producers then run the
+    // regular path (one 256-bit load per row and unit, one bounds test) instead of the two-half pair gather.
+    if (d->pl & 1) hi_plane += 2LL * coutp * kpad;
+    p.pair4 = 0;
+    p.w = d->w / 2; p.x_ld = 8; p.sw = d->sw / 2; p.pl = (d->pl + 1) / 2;
+    kw_eff = upt;
+    upt = 1;
+  }
+  p.wide_loads = !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
+  p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
+  p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
   const __half* lo_plane = hi_plane + (long long)coutp * kpad;
   CUtensorMap mh, ml, my[3];
   int rc = f16::make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
