@@ -117,7 +117,13 @@ def _conv_node(x, w, s, pb, pe, auto_pad='explicit'):
     (2, 64, 56, 192, 3, 1, (1, 1), (1, 1)), (3, 192, 28, 64, 1, 1, (0, 0), (0, 0)), (2, 16, 28, 32, 5, 1, (2, 2), (2, 2)),
     (2, 3, 224, 64, 7, 2, (3, 3), (3, 3)), (2, 832, 7, 384, 1, 1, (0, 0), (0, 0)), (2, 3, 300, 32, 3, 2, (0, 0), (1, 1)),
     (1, 512, 19, 273, 1, 1, (0, 0), (0, 0)), (2, 256, 10, 512, 3, 2, (1, 1), (1, 1)), (4, 1, 28, 64, 3, 1, (1, 1), (1, 1)),
-    (2, 528, 14, 256, 1, 1, (0, 0), (0, 0)), (1, 160, 14, 320, 3, 1, (1, 1), (1, 1)), (5, 24, 9, 12, 1, 1, (0, 0), (0, 0))])
+    (2, 528, 14, 256, 1, 1, (0, 0), (0, 0)), (1, 160, 14, 320, 3, 1, (1, 1), (1, 1)), (5, 24, 9, 12, 1, 1, (0, 0), (0, 0)),
+    # C_in <= 4 stems: two-half pair gather (stride 1 / odd width) and the super-pixel mapping (even stride and width) with
+    # even and odd left padding, even and odd kernel widths
+    (2, 3, 33, 16, 3, 1, (1, 1), (1, 1)), (2, 3, 31, 8, 3, 2, (1, 1), (1, 1)), (2, 3, 32, 16, 5, 2, (2, 2), (2, 2)),
+    (1, 4, 30, 8, 4, 2, (1, 1), (2, 2)), (2, 2, 20, 40, 2, 2, (0, 0), (0, 0)),
+    # 96-column tiles (C_out in (64, 96], (128, 192], (256, 288]) next to 128-column ones, odd slot counts
+    (2, 64, 14, 288, 3, 1, (1, 1), (1, 1)), (2, 32, 14, 96, 1, 1, (0, 0), (0, 0)), (1, 96, 9, 160, 3, 1, (1, 1), (1, 1))])
 def test_conv_layer_shapes_vs_oracle(shape, plugins):
     from oracle import ref_ops
     n, cin, hw, cout, k, s, pb, pe = shape
