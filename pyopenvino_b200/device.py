@@ -32,7 +32,57 @@ def init(device=None):
     torch.cuda.set_device(device)
     _cabi.load()
     _cabi.call('b200ov_init', device)
+    global _numa_cpus
+    _numa_cpus = _gpu_local_cpus(device)
+    if os.environ.get('B200OV_DEBUG_NUMA'):
+        print('[b200ov] GPU {}: staging buffers bound to CPUs {}'.format(device, sorted(_numa_cpus) if _numa_cpus else None), flush=True)
     _initialized = True
+
+
+_numa_cpus = None      # CPUs of the NUMA node this process's GPU hangs off (None: unknown / binding disabled)
+
+
+def _gpu_local_cpus(device):
+    """CPU set of the NUMA node the GPU is attached to (sysfs `local_cpulist` of its PCI function), or None."""
+    if os.environ.get('B200OV_NO_NUMA_BIND'):
+        return None
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = '{:04x}:{:02x}:{:02x}.0'.format(p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open('/sys/bus/pci/devices/{}/local_cpulist'.format(bdf)) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(','):
+            if not part:
+                continue
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus if cpus and cpus != allowed else None
+    except Exception:                       # no sysfs entry, old torch, container without the attribute: leave placement alone
+        return None
+
+
+def pinned_empty(n, dtype=torch.float32, zero=False):
+    """Page-locked host buffer for the H2D / D2H edges, allocated on the NUMA node of this process's GPU: the
+    allocating thread is confined to the GPU-local CPUs while the pages are faulted in (first touch), then gets its
+    affinity back.  With one process per GPU and default placement the staging buffers of some ranks land on the far
+    socket and their copies cross the inter-socket link, which is what limited the 2- and 8-GPU end-to-end numbers."""
+    global _numa_cpus
+    prev = None
+    if _numa_cpus:
+        try:
+            prev = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, _numa_cpus)
+        except OSError:
+            prev = None
+    try:
+        t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=dtype).pin_memory()
+    finally:
+        if prev is not None:
+            os.sched_setaffinity(0, prev)
+    return t
 
 
 def stream():
@@ -144,7 +194,7 @@ class DeviceArray:
         """Host copy in logical layout (the D2H edge of the graph)."""
         from . import kernels
         src = kernels.to_plain(self) if self.layout == 'nhwc' else self
-        host = torch.empty(src.size, dtype=torch.float32).pin_memory() if src.size else torch.empty(0)
+        host = pinned_empty(src.size) if src.size else torch.empty(0)
         if src.size:
             host.copy_(src.t[:src.size], non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -649,7 +649,7 @@ class Executable_Network:
             shape = tuple(node['data']['shape'])
             n = int(np.prod(shape))
             self._static_in[node['name']] = {
-                'host': torch.empty(n, dtype=torch.float32).pin_memory(),
+                'host': dev.pinned_empty(n),
                 'dev': DeviceArray(torch.empty(n, dtype=torch.float32, device='cuda'), shape, 'plain'),
                 'node': node}
         # 1) constants: evaluated once, outside the arena, then frozen
@@ -695,7 +695,7 @@ class Executable_Network:
             self._graph_launches = _cabi.launch_count - launches0
         finally:
             dev.set_arena(None)
-        self._out_host = {name: torch.empty(max(arr.size, 1), dtype=torch.float32).pin_memory()
+        self._out_host = {name: dev.pinned_empty(arr.size)
                           for name, arr in self._static_out.items()}
 
     def stage_inputs(self, inputs: dict = None):
@@ -737,6 +737,7 @@ class Executable_Network:
         that want to fill it in place."""
         import torch
         from . import kernels
+        from . import device as dev
         self._ensure_device()
         if self._graph is None:
             self.infer(inputs)                     # builds the plan, warms up, captures the graph
@@ -746,12 +747,12 @@ class Executable_Network:
             for _ in range(2):
                 rq = {'host': {}, 'dev': {}, 'out_host': {}, 'busy': False, 'inputs': None,
                       'h2d_done': torch.cuda.Event(), 'done': torch.cuda.Event(),
-                      'status': torch.zeros(1, dtype=torch.int32).pin_memory()}
+                      'status': dev.pinned_empty(1, torch.int32, zero=True)}
                 for name, st in self._static_in.items():
-                    rq['host'][name] = torch.empty_like(st['host']).pin_memory()
+                    rq['host'][name] = dev.pinned_empty(st['host'].numel())
                     rq['dev'][name] = torch.empty_like(st['dev'].t)
                 for name, arr in self._static_out.items():
-                    rq['out_host'][name] = torch.empty(max(arr.size, 1), dtype=torch.float32).pin_memory()
+                    rq['out_host'][name] = dev.pinned_empty(arr.size)
                 self._requests.append(rq)
             self._next_request = 0
         slot = self._next_request
@@ -865,7 +866,7 @@ class Executable_Network:
             n = int(node['const']['data'].size)
             items.append((node, total, n))
             total += (n + 63) // 64 * 64
-        host = torch.zeros(max(total, 1), dtype=torch.float32).pin_memory()
+        host = dev.pinned_empty(total, zero=True)
         hv = host.numpy()
         for node, off, n in items:
             hv[off:off + n] = node['const']['data']
