@@ -13,23 +13,27 @@
 // GEMM view (reference: Convolution.py:57-87):  D[M pixels][N cout] = A[M][K] * W[N][K]^T.  K is cut into
 // units of 8 channels of one filter tap (cin padded to 8), 4 units = one 32-wide "slot".
 //
-// Warp roles (512 threads = 4 warpgroups with setmaxnreg budgets, one persistent CTA per SM, static tile schedule):
+// Warp roles (512 threads = 4 warpgroups with setmaxnreg budgets, one persistent CTA per SM, static tile schedule,
+// 128 x BLOCK_N output tiles, BLOCK_N = 32 / 64 / 96 / 128):
 //   warp 12     B loader : TMA loads of the pre-split FP16 weight tiles (hi / lo planes, 64 K-elements per
 //                          stage, 128B swizzle) into a shared-memory ring.
-//   warp 13     MMA      : one thread issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in
-//                          shared memory; tcgen05.commit releases A slots / B stages / accumulators.
-//   warp 14     gate     : waits on every mbarrier a slot depends on, ahead of the MMA warp, and publishes a
-//                          "slots ready" counter (the MMA issue blocks on the tensor-pipe queue, so its own
-//                          waits must be short).
+//   warp 13     MMA      : issues tcgen05.mma.kind::f16 with the A operand in TENSOR MEMORY and B in shared memory;
+//                          tcgen05.commit releases A slots / B stages / accumulators.  The whole warp runs the loop
+//                          converged (election inside the asm blocks, uniform datapath) and waits on NAMED BARRIERS
+//                          only: a shared-memory operation of this warp queues behind the producers' gathers.
+//   warp 14     gate     : polls the mbarriers the MMA warp depends on (weight stage landed; accumulators drained,
+//                          when the epilogue does not signal the MMA warp directly) and forwards them as arrivals
+//                          on the stage's named barrier.
 //   warps 0-7   A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
-//                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split with packed
-//                          FP32 math, and tcgen05.st into a 4-slot TMEM ring.  Two sets of four warps work on
-//                          alternating pairs of slots, running ahead across tile boundaries.  The A operand
-//                          never touches shared memory: the MMA reads of B alone already use ~60% of the
-//                          128 B/clk shared-memory port.
-//   warps 8-11  epilogue : drain the hi*hi accumulator every 64 K-elements into FP32 registers ("promotion",
+//                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split (F2FP, FMUL2,
+//                          mixed-precision FHFMA), and tcgen05.st into a TMEM ring of 4 or 8 slots.  Two sets of
+//                          four warps work on alternating pairs of slots, running ahead across tile boundaries.
+//                          The A operand never touches shared memory: the MMA reads of B alone already use ~60%
+//                          of the 128 B/clk shared-memory port.
+//   warps 8-11  epilogue : drain the hi*hi accumulator every 256 K-elements into FP32 registers ("promotion",
 //                          see below), add the cross terms, bias, activation, stage the tile in shared memory
 //                          and write it with TMA stores (coalesced, asynchronous), overlapping the next tile.
+// DESIGN.md section 5.1 has the measurements behind each of these choices.
 //
 // Accuracy engineering (as in gemm_tcgen05.cu): the tensor core truncates when it adds into the FP32
 // accumulator.  The hi*hi accumulator therefore ping-pongs between two TMEM buffers and is added into
@@ -138,7 +142,6 @@ struct Smem {
   static constexpr int A_SLOTS = a_slots(BLOCK_N);
   static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 8;
   static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
-  static constexpr int READY = TMEM_PTR + 8;                           // gate warp -> MMA warp: slots whose inputs are ready
   static constexpr int TOTAL = TMEM_PTR + 16 + 1024;                   // + slack for the 1024-byte alignment of the base
 };
 
@@ -273,7 +276,6 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       mbar_init(bar_cross_full(i), 1);
       mbar_init(bar_cross_empty(i), NUM_EPILOGUE);
     }
-    *reinterpret_cast<volatile uint32_t*>(base_ptr + L::READY) = 0u;
     fence_mbar_init();
     prefetch_tensormap(&map_hi);
     prefetch_tensormap(&map_lo);
@@ -392,8 +394,8 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       F16_TRACE_STORE(1, lane == 0);
     } else if (warp == W_GATE) {
       // ================= gate ========================================================================
-      // Runs the MMA warp's waits ahead of it: the UTCHMMA issue blocks while the tensor-pipe queue is full,
-      // and four serial mbarrier waits per slot in the issuing thread left the pipe idle half of the time.
+      // Polls the mbarriers the MMA warp depends on, one B stage ahead of it, and forwards each stage as an arrival
+      // on the stage's named barrier (an mbarrier try_wait in the issuing warp itself cost 200-300 cycles).
       static_assert(CHUNK % 2 == 0, "a B stage (two slots) must not straddle promotion chunks");
       uint32_t bcount = 0, chunkcount = 0;
       for (int tl = 0; tl < my_tiles; ++tl) {

@@ -68,31 +68,6 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
-  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_volatile_shared(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-// Spin until the counter at `addr` reaches `target` (bounded like mbar_wait).  A relaxed (volatile) load on purpose:
-// ld.acquire cost the MMA issuer ~200 cycles per slot (it orders against the thread's outstanding tcgen05 traffic);
-// what the flag guards is read by the tensor core (TMEM written with tcgen05.st + wait::st, shared memory written by
-// TMA and completed on an mbarrier the gate warp observed), and the caller issues tcgen05.fence::after_thread_sync.
-__device__ __forceinline__ void wait_ready(uint32_t addr, uint32_t target) {
-  long long t0 = 0;
-  while ((int)(ld_volatile_shared(addr) - target) < 0) {
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -14,6 +14,12 @@
 #include "../../pyopenvino_b200/csrc/tc_ptx.cuh"
 using namespace b200ov::ptx;
 
+__device__ __forceinline__ uint32_t ld_volatile_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
