@@ -101,6 +101,7 @@ struct Params {
   int nseg;
   int seg_col0[3], seg_cout[3], seg_yld[3];
   float* seg_y[3];
+  int prefetch;                        // 1: L2 prefetch of the set's next slot pair (long channel runs, HBM-bound layers)
   int wide_loads;                      // 1: 256-bit gathers (x 32-byte aligned, x_ld % 8 == 0)
   int pair4;                           // 1: cin <= 4 with a pixel pitch of 4 floats: a unit is two horizontally
                                        //    adjacent filter taps x 4 channels (d_upt then divides by units per filter ROW)
@@ -460,6 +461,9 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         for (int r = 0; r < 4; ++r) {
           const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
           dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, WIDE);
+          // the same rows, 16 units (4 slots) further along the channels of this tap: what this set gathers next
+          if (p.prefetch && u4 == 0 && ok && cu + 16 < p.d_upt.d)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase[r] + off + 128));
         }
       } else {
         // two adjacent taps (ky, 2*kxp) and (ky, 2*kxp + 1): with a pixel pitch of 4 floats they are 8 contiguous
@@ -858,6 +862,11 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
     kw_eff = upt;
     upt = 1;
   }
+  // Optional L2 prefetch of what a producer set gathers next (same rows, 16 units further along the channel run), only
+  // where that stays inside one filter tap and the four lanes of a pixel cover one 128-byte line.  +4..10 % on layers
+  // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
+  // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1.
+  { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
   p.wide_loads = !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
   p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
