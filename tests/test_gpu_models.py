@@ -276,3 +276,17 @@ def test_ssd_batch64_records_are_batch1_records(model_dir):
         assert np.array_equal(blk[:, 0:2], ref[:, 0:2]), i          # rank + class id, in order
         ok, msg = close(blk[:, 2:], ref[:, 2:], rtol=1e-4, atol=1e-5)
         assert ok, (i, msg)
+
+
+@pytest.mark.parametrize('model,batch', [('googlenet-v1', 64), ('mnist_bn', 256)])
+def test_replay_is_bit_deterministic(model_dir, model, batch):
+    """The contraction kernel's roles hand work to each other through named barriers, mbarriers and tensor-memory
+    rings; its accumulation order is fixed, so a protocol race would show up as a changing result.  Same batch,
+    40 graph replays, one digest."""
+    import hashlib
+    from tools.synth_bin import synth_input
+    x = synth_input(model, batch=batch, seed=7)
+    net, exe = _load(model_dir, model, batch=batch)
+    name, out = net.inputs[0]['name'], net.outputs[0]['name']
+    digests = {hashlib.sha256(np.ascontiguousarray(exe.infer({name: x})[out]).tobytes()).hexdigest() for _ in range(40)}
+    assert len(digests) == 1
