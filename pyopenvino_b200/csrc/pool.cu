@@ -227,7 +227,8 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
     PoolStripP q;
     q.h = d->h; q.w = d->w; q.pt = d->pt; q.pl = d->pl; q.hp = d->h + d->pt + d->pb;
     q.wpad = d->w + d->pl + d->pr; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld; q.y_ld = d->y_ld;
-    q.th = d->oh < 8 ? d->oh : 8;
+    const int th = d->sh == 1 ? 4 : 8;          // strip height: measured sweep (4 / 8 / 14 / 28) per stride
+    q.th = d->oh < th ? d->oh : th;
     const int tw = d->sh == 1 ? 4 : 2;
     const int strips = ceil_div(d->oh, q.th), cg = d->c / 4, owt = ceil_div(d->ow, tw);
     const long long items = (long long)d->n * strips * owt * cg;
