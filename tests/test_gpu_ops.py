@@ -256,3 +256,14 @@ def test_sibling_1x1_group_matches_separate_convs(plugins):
         ok, msg = close(y.numpy(), want)
         assert ok, msg
     assert outs[0].ld == 256 and outs[0].c_off == 64
+
+
+@pytest.mark.parametrize('tool,cases', [('fuzz_conv.py', 200), ('fuzz_ops.py', 240)])
+def test_randomised_parity_sweeps(tool, cases):
+    """tools/fuzz_conv.py / fuzz_ops.py: random shapes, strides, paddings and fused epilogues against the oracle."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    r = subprocess.run([sys.executable, os.path.join(REPO, 'tools', tool), '--cases', str(cases), '--seed', '11'],
+                       capture_output=True, text=True, cwd=REPO, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
