@@ -102,6 +102,16 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def set_blas_threads():
+    """Give the CPU reference every host core this process may run on, whatever the launcher exported
+    (torchrun sets OMP_NUM_THREADS=1): OpenBLAS' pool is resized at run time.  Returns the limiter (keep it alive)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api='blas')
+    except Exception:
+        return None
+
+
 def time_cpu_port(model, budget_s, min_images=1, max_images=64):
     """Times the oracle port (numpy restatement of the reference engine, kernel_type='special', Const
     re-materialised from python tuples every inference like the reference) batch-1 on the host cores."""
@@ -128,6 +138,7 @@ def run_reference(args, model, desc):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    limiter = set_blas_threads()          # noqa: F841  (explicit: not whatever OMP_NUM_THREADS the launcher exported)
     from oracle import ref_engine
     from tools.synth_bin import ensure_model, synth_input
     xml = ensure_model(model, CACHE)
@@ -150,10 +161,239 @@ def run_reference(args, model, desc):
     line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': desc, 'model': model, 'images_per_step': per_step, 'host_cpus': os.cpu_count()},
-            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'config': {'workload': desc, 'model': model, 'images_per_step': per_step, 'host_cpus': os.cpu_count(),
+                       'blas_threads': cores, 'omp_num_threads_env': os.environ.get('OMP_NUM_THREADS')},
+            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'blas_threads': cores},
             'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+def kernel_of(kind):
+    """layer family -> the CUDA kernel that runs it"""
+    if kind.startswith('conv') or kind == 'matmul':
+        return 'conv_f16x2_kernel'
+    return {'depthwise': 'dwconv3x3_strip_kernel', 'maxpool': 'pool_max_strip_kernel', 'lrn': 'lrn_vec4_kernel',
+            'input_layout': 'nchw_to_nhwc_smallc_kernel'}.get(kind, kind)
+
+
+def layer_table(exe, in_name, x, peaks):
+    """Per-layer roofline: an eager pass of the same fused plan with CUDA events per layer."""
+    from tools import roofline
+    work = roofline.layer_work(exe)
+    steps = exe.profile_steps({in_name: x}, iters=3)
+    tensor_peak = peaks['bf16_tflops_sustained']          # tensor denominator = measured dense bf16 (stated)
+    fam, layers = {}, []
+    total_ms = sum(s['ms'] for s in steps)
+    for s in steps:
+        w = work.get(s['id'])
+        if w is None:
+            continue
+        f = fam.setdefault(w['kind'], {'ms': 0.0, 'flops': 0, 'bytes': 0, 'launches': 0})
+        f['ms'] += s['ms']
+        f['flops'] += w['flops']
+        f['bytes'] += w['bytes']
+        f['launches'] += 1
+        roof = roofline.roofline_ms(w, peaks['hbm_gbs'], tensor_peak)
+        layers.append({'name': s['name'], 'kind': w['kind'], 'ms': s['ms'], 'gflop': w['flops'] / 1e9, 'mbytes': w['bytes'] / 1e6,
+                       'tflops': w['flops'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0.0,
+                       'gbs': w['bytes'] / (s['ms'] * 1e-3) / 1e9 if s['ms'] > 0 else 0.0, 'roofline_ms': roof,
+                       'frac_of_roofline': roof / s['ms'] if s['ms'] > 0 else 0.0})
+    kern = {}
+    for kind, f in fam.items():
+        k = kern.setdefault(kernel_of(kind), {'ms': 0.0, 'flops': 0, 'bytes': 0, 'launches': 0, 'families': []})
+        for key in ('ms', 'flops', 'bytes', 'launches'):
+            k[key] += f[key]
+        k['families'].append(kind)
+    return work, layers, fam, kern, total_ms
+
+
+def kernel_roofline(name, k, total_ms, peaks, model):
+    """The `roofline` object for one kernel (all its launches of a step)."""
+    tensor_peak = peaks['bf16_tflops_sustained']
+    ai = k['flops'] / max(k['bytes'], 1)
+    # the f16x2 contraction spends 3 tensor-core MMAs per FP32 product: its ridge point uses peak / 3
+    mma_per_product = 3 if name == 'conv_f16x2_kernel' else 1
+    tensor_bound = ai > (tensor_peak / mma_per_product) * 1e12 / (peaks['hbm_gbs'] * 1e9)
+    if tensor_bound:
+        achieved = k['flops'] / (k['ms'] * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
+                'mma_per_fp32_product': mma_per_product, 'tensor_pipe_frac': achieved * mma_per_product / tensor_peak}
+    else:
+        achieved = k['bytes'] / (k['ms'] * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs']}
+    traffic = None
+    tpath = os.path.join(REPO, 'profiles', 'ncu_traffic.json')      # dram bytes per launch from an ncu capture of this command
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(model, {}).get(name)
+        except Exception:
+            traffic = None
+    roof.update({'traffic': traffic, 'kernel': name, 'families': sorted(k['families']), 'launches_per_step': k['launches'],
+                 'share_of_step': k['ms'] / total_ms if total_ms else None,
+                 'algorithmic_gflop_per_step': k['flops'] / 1e9, 'algorithmic_mbytes_per_step': k['bytes'] / 1e6,
+                 'algorithmic_mbytes_per_launch': k['bytes'] / 1e6 / max(k['launches'], 1),
+                 'avg_launch_ms': k['ms'] / max(k['launches'], 1), 'peak_source': peaks['source']})
+    if name == 'conv_f16x2_kernel':
+        roof['peak_note'] = ('tensor peak = measured dense bf16 (sustained); an FP32-accurate product costs 3 kind::f16 MMAs '
+                             '(f16x2 split), so tensor_pipe_frac = 3 * achieved / peak is the share of the tensor pipe in use')
+    return roof
+
+
+def time_e2e(exe, in_name, out_name, x, steps, warmup, world, dtype=np.float32):
+    """End to end through the public API with host arrays: every step's batch sits in pinned host memory (the request
+    slot's own buffer, element type `dtype`) and pays its own H2D + graph replay + D2H of the result inside the timed
+    region.  Two requests are kept in flight (start_async / wait), so the H2D of step i+1 overlaps the kernels of step i.
+    The slot is named explicitly, so the zero-copy path does not depend on how many requests ran before."""
+    import torch
+    from pyopenvino_b200 import distributed
+    nreq = exe.NUM_REQUESTS
+    bufs = [exe.request_buffer(s, in_name, dtype) for s in range(nreq)]
+    for b in bufs:
+        b[...] = x
+    for i in range(max(warmup, 1)):
+        exe.wait(exe.start_async({in_name: bufs[i % nreq]}, slot=i % nreq))
+    torch.cuda.synchronize()
+    distributed.barrier()
+    t0 = time.perf_counter()
+    pending, res = None, None
+    for i in range(steps):
+        slot = exe.start_async({in_name: bufs[i % nreq]}, slot=i % nreq)
+        if pending is not None:
+            res = exe.wait(pending)
+            if world > 1:
+                distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
+        pending = slot
+    res = exe.wait(pending)
+    if world > 1:
+        distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
+    torch.cuda.synchronize()
+    return distributed.max_over_ranks(time.perf_counter() - t0), res[out_name]
+
+
+def measure(model, batch, desc, args, peaks, rank, world, local, primary):
+    """One workload at `world` GPUs: device-timed value, e2e (FP32 and uint8 host input), per-layer roofline.
+    Returns the fields of a bench line (rank 0) or None."""
+    import torch
+    from pyopenvino_b200 import distributed
+    from pyopenvino_b200.inference_engine import IECore
+    from tools.synth_bin import ensure_model, synth_input
+
+    if rank == 0:
+        ensure_model(model, CACHE)
+    distributed.barrier()
+    xml = ensure_model(model, CACHE)
+    ie = IECore()
+    net = ie.read_network(xml, xml[:-4] + '.bin')
+    exe = ie.load_network(net, 'B200', batch_size=batch)
+    if args.math:
+        exe.kernel_type = args.math
+    in_name, out_name = net.inputs[0]['name'], net.outputs[0]['name']
+    x = synth_input(model, batch=batch, seed=1 + rank)       # every rank owns different images
+    if model == 'mnist':
+        x = x * np.float32(255.0)
+    exe.broadcast_constants(src=0)                            # rank 0's weights are the replica everyone uses
+    out = exe.infer({in_name: x})[out_name]                   # builds the plan, warms up, captures the CUDA graph
+    launches_per_step = exe.kernels_per_inference()
+    out_dev = exe._static_out[out_name]
+    steps, warmup = args.steps, args.warmup
+
+    def step_resident():
+        exe.replay()
+        if world > 1:
+            distributed.gather_outputs(out_dev.t[:out_dev.size].view(out_dev.shape[0], -1))
+
+    def timed(nsteps, sampler=None):
+        distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.__enter__()
+        e0.record()
+        for _ in range(nsteps):
+            step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.__exit__(None, None, None)
+        distributed.barrier()
+        return distributed.max_over_ranks(e0.elapsed_time(e1))
+
+    sampler = ClockSampler(local)
+    res = {}
+    with torch.cuda.stream(exe.stream):
+        exe.stage_inputs({in_name: x})
+        for _ in range(warmup):
+            step_resident()
+        exe.stream.synchronize()
+        ms_total = timed(steps, sampler)
+        ms_step = ms_total / steps
+        # the same replay loop held for >= args.sustain seconds: does the number survive the power limit?
+        sustained = None
+        if args.sustain > 0 and (primary or args.sustain_all):
+            n_sus = max(steps, int(args.sustain * 1e3 / max(ms_step, 1e-3)) + 1)
+            sus_sampler = ClockSampler(local)
+            ms_sus = timed(n_sus, sus_sampler)
+            sustained = {'value': batch * world * n_sus / (ms_sus * 1e-3), 'unit': 'images/s', 'steps': n_sus, 'seconds': ms_sus * 1e-3,
+                         'ms_per_step': ms_sus / n_sus, 'clocks': sus_sampler.summary()}
+        # end to end, FP32 host arrays (headline) ...
+        e2e_s, _ = time_e2e(exe, in_name, out_name, x, steps, warmup, world, np.float32)
+        # ... and the same images as uint8 frames (1 byte per value over PCIe; widened in the layout kernel)
+        x8 = np.clip(np.rint(x if model in ('mnist', 'ssd_mobilenet_v1_coco') else x * 255.0), 0, 255).astype(np.uint8)
+        e2e8_s, _ = time_e2e(exe, in_name, out_name, x8, steps, warmup, world, np.uint8)
+        exe._select_graph({in_name: x})
+        # one synchronous infer() per step (no overlap), reported beside it
+        x_pinned = exe.input_buffer(in_name)
+        x_pinned[...] = x
+        exe.infer({in_name: x_pinned})
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            exe.infer({in_name: x_pinned})
+        torch.cuda.synchronize()
+        e2e_sync_s = distributed.max_over_ranks(time.perf_counter() - t0)
+    distributed.barrier()
+
+    images = batch * world * steps
+    res = {'value': images / (ms_total * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_step}
+    if rank != 0:
+        del exe
+        return None
+    work, layers, fam, kern, total_ms = layer_table(exe, in_name, x, peaks)
+    top_kind = max(kern, key=lambda k: kern[k]['ms'])
+    res['roofline'] = kernel_roofline(top_kind, kern[top_kind], total_ms, peaks, model)
+    res['kernel_rooflines'] = {k: kernel_roofline(k, v, total_ms, peaks, model) for k, v in kern.items()
+                               if k in ('conv_f16x2_kernel', 'dwconv3x3_strip_kernel', 'pool_max_strip_kernel', 'lrn_vec4_kernel')
+                               and k != top_kind and v['ms'] > 0}
+    model_roof_ms = sum(l['roofline_ms'] for l in layers)
+    res['model_roofline'] = {'sum_layer_roofline_ms': model_roof_ms, 'frac': model_roof_ms / ms_step,
+                             'families': {k: {'ms': v['ms'], 'share': v['ms'] / total_ms, 'tflops': v['flops'] / (v['ms'] * 1e-3) / 1e12,
+                                              'gbs': v['bytes'] / (v['ms'] * 1e-3) / 1e9} for k, v in fam.items() if v['ms'] > 0}}
+    if args.layers_out and primary:
+        os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+        json.dump({'workload': desc, 'batch': batch, 'layers': layers, 'families': res['model_roofline']['families']},
+                  open(args.layers_out, 'w'), indent=1)
+    working_set_mb = sum(w['bytes'] for w in work.values()) / 1e6
+    res['config'] = {'workload': desc, 'model': model, 'batch_per_gpu': batch, 'global_batch': batch * world,
+                     'input_shape': list(x.shape), 'parallelism': 'dp{} (batch-sharded replicas, no data-path collective)'.format(world),
+                     'l2': 'no flush: per-step working set {:.0f} MB > 126 MB L2'.format(working_set_mb)
+                     if working_set_mb > 126 else 'working set {:.0f} MB fits L2 (not flushed)'.format(working_set_mb),
+                     'fused_cuda_graph': True, 'math': args.math or 'auto',
+                     'arena_mb': exe._arena.bytes() / 1e6 if exe._arena is not None else None}
+    res['clocks'] = sampler.summary()
+    if sustained is not None:
+        res['sustained'] = sustained
+    api = 'Executable_Network.start_async(slot=) / wait, 2 requests in flight (H2D of step i+1 overlaps step i)'
+    res['e2e'] = {'value': images / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(x.nbytes) * world,
+                  'd2h_bytes_per_step': int(out.nbytes) * world, 'ms_per_step': e2e_s / steps * 1e3, 'input_dtype': 'float32',
+                  'api': api, 'sync_infer_value': images / e2e_sync_s, 'sync_infer_ms_per_step': e2e_sync_s / steps * 1e3}
+    res['e2e_u8'] = {'value': images / e2e8_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(x8.nbytes) * world,
+                     'd2h_bytes_per_step': int(out.nbytes) * world, 'ms_per_step': e2e8_s / steps * 1e3, 'input_dtype': 'uint8',
+                     'api': api, 'note': 'same images as uint8 frames (Parameter.py:13 accepts any array-like); widened on the device'}
+    res['gpu_launches'] = launches_per_step * steps
+    res['launches_per_step'] = launches_per_step
+    del exe
+    return res
 
 
 def main():
@@ -167,6 +407,9 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for cpu_baseline')
     ap.add_argument('--layers-out', default=None, help='write the per-layer roofline table (JSON) here')
     ap.add_argument('--math', default=None, choices=[None, 'fp32', 'tf32x3', 'tf32', 'f16x2', 'safe'])
+    ap.add_argument('--sustain', type=float, default=3.0, help='seconds of back-to-back replays for the `sustained` field (0 = off)')
+    ap.add_argument('--sustain-all', action='store_true', help='also for the secondary workloads')
+    ap.add_argument('--no-secondary', action='store_true', help='measure only --workload')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     model, default_batch, desc = WORKLOADS[args.workload]
@@ -176,190 +419,39 @@ def main():
     batch = args.batch or default_batch
 
     import torch
-    from pyopenvino_b200 import _cabi, distributed
-    from pyopenvino_b200.inference_engine import IECore
-    from tools import roofline
-    from tools.synth_bin import ensure_model, synth_input
+    from pyopenvino_b200 import device, distributed
 
     rank, world, local = distributed.init()
     assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node {}'.format(args.gpus)
     torch.cuda.set_device(local)
+    if world > 1:
+        device.bind_host_thread(local, world)                  # each rank's python thread on its own slice of the host CPUs
     peaks = load_peaks()
 
+    line = {'metric': METRIC, 'value': None, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic'}
+    res = measure(model, batch, desc, args, peaks, rank, world, local, primary=True)
     if rank == 0:
-        xml = ensure_model(model, CACHE)
-    distributed.barrier()
-    xml = ensure_model(model, CACHE)
-    ie = IECore()
-    net = ie.read_network(xml, xml[:-4] + '.bin')
-    exe = ie.load_network(net, 'B200', batch_size=batch)
-    if args.math:
-        exe.kernel_type = args.math
-    in_name, out_name = net.inputs[0]['name'], net.outputs[0]['name']
-    x = synth_input(model, batch=batch, seed=1 + rank)       # every rank owns different images
-    if model == 'mnist':
-        x = x * np.float32(255.0)
-    flat = exe.load_constants()
-    distributed.broadcast_weights(flat)                       # rank 0's weights are the replica everyone uses
-    out = exe.infer({in_name: x})[out_name]                   # builds the plan, warms up, captures the CUDA graph
-    launches_per_step = exe.kernels_per_inference()
-    out_dev = exe._static_out[out_name]
-
-    def step_resident():
-        exe.replay()
-        if world > 1:
-            distributed.gather_outputs(out_dev.t[:out_dev.size].view(out_dev.shape[0], -1))
-
-    sampler = ClockSampler(local)
-    with torch.cuda.stream(exe.stream):
-        exe.stage_inputs({in_name: x})
-        for _ in range(args.warmup):
-            step_resident()
-        exe.stream.synchronize()
-        distributed.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with sampler:
-            e0.record()
-            for _ in range(args.steps):
-                step_resident()
-            e1.record()
-            torch.cuda.synchronize()
-        distributed.barrier()
-        ms_total = distributed.max_over_ranks(e0.elapsed_time(e1))
-
-        # end to end through the public API with host arrays: every step's batch sits in pinned host memory and
-        # pays its own H2D + graph replay + D2H of the result inside the timed region.  Two requests are kept in
-        # flight (Executable_Network.start_async / wait), so the H2D of step i+1 overlaps the kernels of step i.
-        s0 = exe.start_async({in_name: x})
-        exe.wait(s0)
-        bufs = [exe.request_buffer(0, in_name), exe.request_buffer(1, in_name)]
-        for b in bufs:
-            b[...] = x
-        for _ in range(args.warmup):
-            exe.wait(exe.start_async({in_name: bufs[0]}))
-        torch.cuda.synchronize()
-        distributed.barrier()
-        t0 = time.perf_counter()
-        pending = None
-        for i in range(args.steps):
-            slot = exe.start_async({in_name: bufs[i & 1]})
-            if pending is not None:
-                res = exe.wait(pending)
-                if world > 1:
-                    distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
-            pending = slot
-        res = exe.wait(pending)
-        if world > 1:
-            distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
-        torch.cuda.synchronize()
-        e2e_s = distributed.max_over_ranks(time.perf_counter() - t0)
-        # the same, one synchronous infer() per step (no overlap), reported beside it
-        x_pinned = exe.input_buffer(in_name)
-        x_pinned[...] = x
-        exe.infer({in_name: x_pinned})
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            exe.infer({in_name: x_pinned})
-        torch.cuda.synchronize()
-        e2e_sync_s = distributed.max_over_ranks(time.perf_counter() - t0)
-    distributed.barrier()
-
-    images = batch * world * args.steps
-    value = images / (ms_total * 1e-3)
-    e2e_value = images / e2e_s
-
-    line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic'}
-
-    if rank == 0:
-        # ---- per-layer roofline: eager pass of the same fused plan with CUDA events per layer --------
-        work = roofline.layer_work(exe)
-        steps = exe.profile_steps({in_name: x}, iters=3)
-        tf32x3_peak = peaks['bf16_tflops_sustained']          # tensor denominator = measured dense bf16 (stated)
-        fam = {}
-        layers = []
-        total_ms = sum(s['ms'] for s in steps)
-        for s in steps:
-            w = work.get(s['id'])
-            if w is None:
+        line.update(res)
+    # the other BASELINE.json configurations, same run, same N (the driver only ever launches the default command)
+    secondary = {}
+    if not args.no_secondary and args.batch is None:
+        for name in ('ssd_mobilenet_v1_coco', 'mnist_bn', 'mnist'):
+            if name == args.workload:
                 continue
-            f = fam.setdefault(w['kind'], {'ms': 0.0, 'flops': 0, 'bytes': 0, 'launches': 0})
-            f['ms'] += s['ms']
-            f['flops'] += w['flops']
-            f['bytes'] += w['bytes']
-            f['launches'] += 1
-            roof = roofline.roofline_ms(w, peaks['hbm_gbs'], tf32x3_peak)
-            layers.append({'name': s['name'], 'kind': w['kind'], 'ms': s['ms'], 'gflop': w['flops'] / 1e9, 'mbytes': w['bytes'] / 1e6,
-                           'tflops': w['flops'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0.0,
-                           'gbs': w['bytes'] / (s['ms'] * 1e-3) / 1e9 if s['ms'] > 0 else 0.0, 'roofline_ms': roof,
-                           'frac_of_roofline': roof / s['ms'] if s['ms'] > 0 else 0.0})
-        # families -> the CUDA kernel that runs them; the roofline object describes the dominant KERNEL
-        def kernel_of(kind):
-            if kind.startswith('conv') or kind == 'matmul':
-                return 'conv_f16x2_kernel'
-            return {'depthwise': 'dwconv3x3_strip_kernel', 'maxpool': 'pool_max_strip_kernel', 'lrn': 'lrn_vec4_kernel',
-                    'input_layout': 'nchw_to_nhwc_smallc_kernel'}.get(kind, kind)
-        kern = {}
-        for kind, f in fam.items():
-            k = kern.setdefault(kernel_of(kind), {'ms': 0.0, 'flops': 0, 'bytes': 0, 'launches': 0, 'families': []})
-            for key in ('ms', 'flops', 'bytes', 'launches'):
-                k[key] += f[key]
-            k['families'].append(kind)
-        top_kind = max(kern, key=lambda k: kern[k]['ms'])
-        top = kern[top_kind]
-        ai = top['flops'] / max(top['bytes'], 1)
-        # the f16x2 contraction spends 3 tensor-core MMAs per FP32 product: its ridge point uses peak / 3
-        mma_per_product = 3 if top_kind == 'conv_f16x2_kernel' else 1
-        tensor_bound = ai > (tf32x3_peak / mma_per_product) * 1e12 / (peaks['hbm_gbs'] * 1e9)
-        if tensor_bound:
-            achieved = top['flops'] / (top['ms'] * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32x3_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32x3_peak,
-                    'mma_per_fp32_product': mma_per_product, 'tensor_pipe_frac': achieved * mma_per_product / tf32x3_peak}
-        else:
-            achieved = top['bytes'] / (top['ms'] * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs']}
-        traffic = None
-        tpath = os.path.join(REPO, 'profiles', 'ncu_traffic.json')      # dram bytes per launch from an ncu capture of this command
-        if os.path.isfile(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(model, {}).get(top_kind)
-            except Exception:
-                traffic = None
-        roof.update({'traffic': traffic, 'kernel': top_kind, 'families': sorted(top['families']), 'launches_per_step': top['launches'],
-                     'share_of_step': top['ms'] / total_ms if total_ms else None,
-                     'algorithmic_gflop_per_step': top['flops'] / 1e9, 'algorithmic_mbytes_per_step': top['bytes'] / 1e6,
-                     'algorithmic_mbytes_per_launch': top['bytes'] / 1e6 / max(top['launches'], 1),
-                     'avg_launch_ms': top['ms'] / max(top['launches'], 1), 'peak_source': peaks['source'],
-                     'peak_note': 'tensor peak = measured dense bf16 (sustained); an FP32-accurate product costs 3 kind::f16 MMAs '
-                                  '(f16x2 split), so tensor_pipe_frac = 3 * achieved / peak is the share of the tensor pipe in use'})
-        model_roof_ms = sum(l['roofline_ms'] for l in layers)
-        line['roofline'] = roof
-        line['model_roofline'] = {'sum_layer_roofline_ms': model_roof_ms, 'frac': model_roof_ms / (ms_total / args.steps),
-                                  'families': {k: {'ms': v['ms'], 'share': v['ms'] / total_ms, 'tflops': v['flops'] / (v['ms'] * 1e-3) / 1e12,
-                                                   'gbs': v['bytes'] / (v['ms'] * 1e-3) / 1e9} for k, v in fam.items() if v['ms'] > 0}}
-        if args.layers_out:
-            os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
-            json.dump({'workload': desc, 'batch': batch, 'layers': layers, 'families': line['model_roofline']['families']},
-                      open(args.layers_out, 'w'), indent=1)
-        working_set_mb = sum(w['bytes'] for w in work.values()) / 1e6
-        line['config'] = {'workload': desc, 'model': model, 'batch_per_gpu': batch, 'global_batch': batch * world,
-                          'input_shape': list(x.shape), 'parallelism': 'dp{} (batch-sharded replicas, no data-path collective)'.format(world),
-                          'l2': 'no flush: per-step working set {:.0f} MB > 126 MB L2'.format(working_set_mb)
-                          if working_set_mb > 126 else 'working set {:.0f} MB fits L2 (not flushed)'.format(working_set_mb),
-                          'fused_cuda_graph': True, 'math': args.math or 'auto'}
-        line['clocks'] = sampler.summary()
-        line['e2e'] = {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x.nbytes) * world,
-                       'd2h_bytes_per_step': int(out.nbytes) * world, 'ms_per_step': e2e_s / args.steps * 1e3,
-                       'api': 'Executable_Network.start_async / wait, 2 requests in flight (H2D of step i+1 overlaps step i)',
-                       'sync_infer_value': images / e2e_sync_s, 'sync_infer_ms_per_step': e2e_sync_s / args.steps * 1e3}
-        line['gpu_launches'] = launches_per_step * args.steps
-        line['launches_per_step'] = launches_per_step
+            m2, b2, d2 = WORKLOADS[name]
+            r2 = measure(m2, b2, d2, args, peaks, rank, world, local, primary=False)
+            if rank == 0:
+                keep = ('value', 'unit', 'ms_per_step', 'e2e', 'e2e_u8', 'roofline', 'kernel_rooflines', 'model_roofline', 'config',
+                        'clocks', 'launches_per_step', 'sustained')
+                secondary[name] = {k: r2[k] for k in keep if k in r2}
+    if rank == 0:
+        if secondary:
+            line['secondary'] = secondary
         if world == 1:
+            limiter = set_blas_threads()      # noqa: F841
             ips, n, dt = time_cpu_port(model, args.cpu_budget)
-            line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': blas_threads(), 'kind': 'port',
+            line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': blas_threads(), 'kind': 'port', 'blas_threads': blas_threads(),
                                     'sample': '{} batch-1 inferences in {:.1f} s, oracle port of the reference engine, kernel_type=special, '
                                               'Const rebuilt per inference, host_cpus={}'.format(n, dt, os.cpu_count())}
         print(json.dumps(line), flush=True)

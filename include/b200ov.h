@@ -210,6 +210,16 @@ int b200ov_transpose(const float* x, float* y, int batch, int rows, int cols, in
 int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, int y_ld,
                                int has_scale, const float* scale_vec, float scale_s,
                                int has_shift, const float* shift_vec, float shift_s, void* stream);
+/* Element types a host input may arrive in.  Parameter.compute casts whatever array-like it is given with
+ * `np.array(param).reshape(shape).astype(precision)` (Parameter.py:13; draw-and-infer.py:56-60 feeds uint8): here the
+ * bytes cross PCIe in their native width and are widened on the device (exact, so bit-identical to the host cast). */
+enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3 };
+/* b200ov_nchw_to_nhwc_affine for an input of element type `dtype` (NCHW, dense). */
+int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int hw, int y_ld,
+                         int has_scale, const float* scale_vec, float scale_s,
+                         int has_shift, const float* shift_vec, float shift_s, void* stream);
+/* y[i] = (float)x[i]: a non-image (not 4-D) input of element type `dtype` (Parameter.py:13). */
+int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream);
 /* rows x cols strided copy (Concat.py:9-13 when producers could not write in place). */
 int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream);
 

@@ -2,14 +2,26 @@
 // Parameter pre-processing (NCHW -> NHWC with per-channel scale / shift) and strided row copies
 // (Concat when a producer could not write in place).  All bandwidth-bound; the transposes go
 // through a padded 32x32 shared-memory tile so both the read and the write are coalesced.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace b200ov {
 
+// Host inputs arrive in their native width (uint8 camera frames, FP16, FP32; Parameter.py:13 casts with
+// `.astype(precision)`) and are widened here, on the device, instead of on the host before the PCIe copy.
+// Every widening is exact, so the result is bit-identical to the reference's host-side cast.
+__device__ __forceinline__ float widen(float v) { return v; }
+__device__ __forceinline__ float widen(__half v) { return __half2float(v); }
+__device__ __forceinline__ float widen(uint8_t v) { return (float)v; }
+__device__ __forceinline__ float widen(int8_t v) { return (float)v; }
+template <typename T>
+__device__ __forceinline__ float load_widen(const T* p) { return widen(__ldg(p)); }
+
 // x: [batch][rows][x_ld] (cols valid)  ->  y: [batch][cols][y_ld] (rows valid)
 // AFFINE: v = v*scale[row] + shift[row] (row = source row = channel of an NCHW tensor)
-template <bool AFFINE>
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int rows,
+template <bool AFFINE, typename TIN = float>
+__global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ x, float* __restrict__ y, int rows,
                                                         int cols, int x_ld, int y_ld, int tiles_r, int tiles_c,
                                                         int has_scale, const float* __restrict__ scale_vec,
                                                         float scale_s, int has_shift,
@@ -20,7 +32,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   bid /= tiles_c;
   const int tr = (int)(bid % tiles_r);
   const int b = (int)(bid / tiles_r);
-  const float* xb = x + (long long)b * rows * x_ld;
+  const TIN* xb = x + (long long)b * rows * x_ld;
   float* yb = y + (long long)b * cols * y_ld;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
@@ -28,7 +40,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     int r = tr * 32 + ty + i, c = tc * 32 + tx;
     float v = 0.f;
     if (r < rows && c < cols) {
-      v = __ldg(xb + (long long)r * x_ld + c);
+      v = load_widen(xb + (long long)r * x_ld + c);
       if (AFFINE) {
         if (has_scale) v = __fmul_rn(v, scale_vec ? __ldg(scale_vec + r) : scale_s);
         if (has_shift) v = __fadd_rn(v, shift_vec ? __ldg(shift_vec + r) : shift_s);
@@ -48,8 +60,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 // of its 32-row tile here; instead a thread owns one pixel, reads its C planes (coalesced across the warp)
 // and writes the pixel's channel run.  PAD = 4 / 8: y_ld == PAD >= C, 128-bit stores with the unused lanes
 // zeroed (the tcgen05 stem convolution gathers whole 8-channel runs and needs finite padding).
-template <int MAXC, int PAD>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* __restrict__ x, float* __restrict__ y,
+template <int MAXC, int PAD, typename TIN = float>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TIN* __restrict__ x, float* __restrict__ y,
                                                                   long long pixels, int c, int hw, int y_ld, int has_scale,
                                                                   const float* __restrict__ scale_vec, float scale_s,
                                                                   int has_shift, const float* __restrict__ shift_vec,
@@ -64,13 +76,13 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* _
        pix += (long long)gridDim.x * blockDim.x) {
     const long long img = pix / hw;
     const int r = (int)(pix - img * hw);
-    const float* xp = x + img * c * hw + r;
+    const TIN* xp = x + img * c * hw + r;
     float v[MAXC];
 #pragma unroll
     for (int ch = 0; ch < MAXC; ++ch) {
       v[ch] = 0.f;
       if (ch < c) {
-        v[ch] = __ldg(xp + (long long)ch * hw);
+        v[ch] = load_widen(xp + (long long)ch * hw);
         if (has_scale) v[ch] = __fmul_rn(v[ch], sc[ch]);
         if (has_shift) v[ch] = __fadd_rn(v[ch], sf[ch]);
       }
@@ -85,6 +97,48 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* _
       for (int ch = 0; ch < MAXC; ++ch)
         if (ch < c) y[pix * y_ld + ch] = v[ch];
     }
+  }
+}
+
+// The same for 1-byte inputs (uint8 / int8), four adjacent pixels per thread: one 32-bit load per plane (128 B per
+// warp and plane instead of 32 B) and four 128-bit stores.  Needs hw % 4 == 0, a 4-byte aligned source and y_ld == 4.
+template <typename TIN>
+__global__ void __launch_bounds__(256) nchw8_to_nhwc4_x4_kernel(const TIN* __restrict__ x, float* __restrict__ y,
+                                                                long long quads, int c, int hw, int has_scale,
+                                                                const float* __restrict__ scale_vec, float scale_s,
+                                                                int has_shift, const float* __restrict__ shift_vec,
+                                                                float shift_s) {
+  float sc[4], sf[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    sc[ch] = (has_scale && ch < c) ? (scale_vec ? __ldg(scale_vec + ch) : scale_s) : 1.f;
+    sf[ch] = (has_shift && ch < c) ? (shift_vec ? __ldg(shift_vec + ch) : shift_s) : 0.f;
+  }
+  const int qhw = hw >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const long long img = q / qhw;
+    const int r = (int)(q - img * qhw) * 4;
+    const TIN* xp = x + img * c * hw + r;
+    float v[4][4];                                   // [pixel][channel]
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t word = 0;
+      if (ch < c) word = __ldg(reinterpret_cast<const uint32_t*>(xp + (long long)ch * hw));
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float f = 0.f;
+        if (ch < c) {
+          const uint32_t b = (word >> (8 * px)) & 0xffu;
+          f = sizeof(TIN) == 1 && TIN(-1) < TIN(0) ? (float)(int8_t)b : (float)b;
+          if (has_scale) f = __fmul_rn(f, sc[ch]);
+          if (has_shift) f = __fadd_rn(f, sf[ch]);
+        }
+        v[px][ch] = f;
+      }
+    }
+    float4* yp = reinterpret_cast<float4*>(y + (img * hw + r) * 4);
+#pragma unroll
+    for (int px = 0; px < 4; ++px) yp[px] = make_float4(v[px][0], v[px][1], v[px][2], v[px][3]);
   }
 }
 
@@ -121,6 +175,47 @@ static int launch_transpose(bool affine, const float* x, float* y, int batch, in
   return B200OV_OK;
 }
 
+template <typename TIN>
+static int input_to_nhwc_typed(const TIN* x, float* y, int n, int c, int hw, int y_ld, int has_scale, const float* scale_vec,
+                               float scale_s, int has_shift, const float* shift_vec, float shift_s, cudaStream_t s) {
+  if (c <= 4) {
+    const long long pixels = (long long)n * hw;
+    if constexpr (sizeof(TIN) == 1) {
+      if (y_ld == 4 && aligned16(y) && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3u) == 0) {
+        nchw8_to_nhwc4_x4_kernel<TIN><<<bw_grid(pixels / 4, 256), 256, 0, s>>>(x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
+                                                                              has_shift, shift_vec, shift_s);
+        B200OV_LAUNCH_CHECK("nchw8_to_nhwc4_x4_kernel");
+        return B200OV_OK;
+      }
+    }
+    if (y_ld == 8 && aligned16(y))
+      nchw_to_nhwc_smallc_kernel<4, 8, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                                scale_s, has_shift, shift_vec, shift_s);
+    else if (y_ld == 4 && aligned16(y))
+      nchw_to_nhwc_smallc_kernel<4, 4, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                                scale_s, has_shift, shift_vec, shift_s);
+    else
+      nchw_to_nhwc_smallc_kernel<4, 0, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+                                                                                scale_s, has_shift, shift_vec, shift_s);
+    B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
+    return B200OV_OK;
+  }
+  const int tiles_r = ceil_div(c, 32), tiles_c = ceil_div(hw, 32);
+  const long long blocks = (long long)n * tiles_r * tiles_c;
+  if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "input_to_nhwc: grid too large");
+  transpose_kernel<true, TIN><<<(unsigned)blocks, 256, 0, s>>>(x, y, c, hw, hw, y_ld, tiles_r, tiles_c, has_scale, scale_vec,
+                                                              scale_s, has_shift, shift_vec, shift_s);
+  B200OV_LAUNCH_CHECK("transpose_kernel");
+  return B200OV_OK;
+}
+
+// plain (non 4-D) inputs: widen only
+template <typename TIN>
+__global__ void __launch_bounds__(256) widen_kernel(const TIN* __restrict__ x, float* __restrict__ y, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    y[i] = load_widen(x + i);
+}
+
 }  // namespace b200ov
 
 using namespace b200ov;
@@ -135,24 +230,47 @@ int b200ov_transpose(const float* x, float* y, int batch, int rows, int cols, in
 int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, int y_ld, int has_scale,
                                const float* scale_vec, float scale_s, int has_shift, const float* shift_vec,
                                float shift_s, void* stream) {
-  B200OV_REQUIRE(x && y && n >= 0 && c > 0 && hw > 0 && y_ld >= c, "nchw_to_nhwc_affine: bad argument");
-  if (c <= 4 && n > 0) {
-    const long long pixels = (long long)n * hw;
-    cudaStream_t s = as_stream(stream);
-    if (y_ld == 8 && aligned16(y))
-      nchw_to_nhwc_smallc_kernel<4, 8><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
-                                                                           scale_s, has_shift, shift_vec, shift_s);
-    else if (y_ld == 4 && aligned16(y))
-      nchw_to_nhwc_smallc_kernel<4, 4><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
-                                                                              scale_s, has_shift, shift_vec, shift_s);
-    else
-      nchw_to_nhwc_smallc_kernel<4, 0><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
-                                                                               scale_s, has_shift, shift_vec, shift_s);
-    B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
-    return B200OV_OK;
+  return b200ov_input_to_nhwc(x, B200OV_DT_F32, y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift, shift_vec,
+                              shift_s, stream);
+}
+
+int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int hw, int y_ld, int has_scale,
+                         const float* scale_vec, float scale_s, int has_shift, const float* shift_vec, float shift_s,
+                         void* stream) {
+  B200OV_REQUIRE(x && y && n >= 0 && c > 0 && hw > 0 && y_ld >= c, "input_to_nhwc: bad argument");
+  B200OV_REQUIRE(dtype == B200OV_DT_F32 || dtype == B200OV_DT_F16 || dtype == B200OV_DT_U8 || dtype == B200OV_DT_I8,
+                 "input_to_nhwc: unknown element type %d", dtype);
+  if (n == 0) return B200OV_OK;
+  switch (dtype) {
+    case B200OV_DT_F16:
+      return input_to_nhwc_typed(static_cast<const __half*>(x), y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift,
+                                 shift_vec, shift_s, as_stream(stream));
+    case B200OV_DT_U8:
+      return input_to_nhwc_typed(static_cast<const uint8_t*>(x), y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift,
+                                 shift_vec, shift_s, as_stream(stream));
+    case B200OV_DT_I8:
+      return input_to_nhwc_typed(static_cast<const int8_t*>(x), y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift,
+                                 shift_vec, shift_s, as_stream(stream));
+    default:
+      return input_to_nhwc_typed(static_cast<const float*>(x), y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift,
+                                 shift_vec, shift_s, as_stream(stream));
   }
-  return launch_transpose(true, x, y, n, c, hw, hw, y_ld, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s,
-                          as_stream(stream));
+}
+
+int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream) {
+  B200OV_REQUIRE(x && y && count >= 0, "widen: bad argument");
+  if (count == 0) return B200OV_OK;
+  cudaStream_t s = as_stream(stream);
+  const int g = bw_grid(count, 256);
+  switch (dtype) {
+    case B200OV_DT_F32: B200OV_CUDA(cudaMemcpyAsync(y, x, (size_t)count * 4, cudaMemcpyDeviceToDevice, s)); return B200OV_OK;
+    case B200OV_DT_F16: widen_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(x), y, count); break;
+    case B200OV_DT_U8: widen_kernel<<<g, 256, 0, s>>>(static_cast<const uint8_t*>(x), y, count); break;
+    case B200OV_DT_I8: widen_kernel<<<g, 256, 0, s>>>(static_cast<const int8_t*>(x), y, count); break;
+    default: return set_error(B200OV_ERR_INVALID, "widen: unknown element type %d", dtype);
+  }
+  B200OV_LAUNCH_CHECK("widen_kernel");
+  return B200OV_OK;
 }
 
 int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream) {

@@ -64,6 +64,29 @@ def _gpu_local_cpus(device):
         return None
 
 
+def bind_host_thread(local_rank, local_world):
+    """One process per GPU on one host: give each rank's python thread its own slice of the host CPUs (the GPU-local
+    NUMA node's when sysfs exposes it, else an even split of the allowed set), so eight launch loops and their pinned
+    staging copies do not migrate over each other.  Returns the CPU set or None when nothing was changed."""
+    if os.environ.get('B200OV_NO_NUMA_BIND'):
+        return None
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        local = _gpu_local_cpus(local_rank) if torch.cuda.is_available() else None
+        pool = sorted(local) if local else allowed
+        share = max(1, len(pool) // max(1, local_world))
+        if local:
+            # ranks whose GPUs share a NUMA node share its CPUs: split by position among all ranks (upper bound on sharers)
+            start = (local_rank * share) % len(pool)
+        else:
+            start = (local_rank * share) % len(pool)
+        mine = set(pool[start:start + share]) or set(pool)
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (OSError, AttributeError):
+        return None
+
+
 def pinned_empty(n, dtype=torch.float32, zero=False):
     """Page-locked host buffer for the H2D / D2H edges, allocated on the NUMA node of this process's GPU: the
     allocating thread is confined to the GPU-local CPUs while the pages are faulted in (first touch), then gets its
@@ -145,6 +168,10 @@ def set_arena(arena):
     _arena = arena
 
 
+def current_arena():
+    return _arena
+
+
 def alloc_f32(nfloats):
     if _arena is not None:
         return _arena.alloc(nfloats)
@@ -206,6 +233,47 @@ class DeviceArray:
 
     def __repr__(self):
         return 'DeviceArray(shape={}, layout={}, ld={}, c_off={})'.format(self.shape, self.layout, self.ld, self.c_off)
+
+
+class RawInput:
+    """A host input staged in HBM in its native element type (uint8 / int8 / float16 / float32), logical IR shape,
+    row-major.  Only the Parameter plugin consumes it: the widening to float32 happens inside the layout kernel
+    (`b200ov_input_to_nhwc`), i.e. after the PCIe copy, and is exact (`Parameter.py:13` does the same cast on the host)."""
+    __slots__ = ('t', 'shape', 'np_dtype')
+    CODES = {np.dtype(np.float32): _cabi.DT_F32, np.dtype(np.float16): _cabi.DT_F16, np.dtype(np.uint8): _cabi.DT_U8,
+             np.dtype(np.int8): _cabi.DT_I8}
+    TORCH = {np.dtype(np.float32): torch.float32, np.dtype(np.float16): torch.float16, np.dtype(np.uint8): torch.uint8,
+             np.dtype(np.int8): torch.int8}
+
+    def __init__(self, t, shape, np_dtype):
+        self.t = t
+        self.shape = tuple(int(s) for s in shape)
+        self.np_dtype = np.dtype(np_dtype)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    @property
+    def code(self):
+        return self.CODES[self.np_dtype]
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if len(self.shape) else 1
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+
+def native_input(val):
+    """Host array-like -> C-contiguous ndarray in the element type that crosses PCIe: uint8 / int8 / float16 /
+    float32 stay as they are, everything else is cast to float32 on the host like the reference (`Parameter.py:13`)."""
+    a = np.asarray(val)
+    if a.dtype not in RawInput.CODES:
+        a = a.astype(np.float32)
+    return a
 
 
 def is_device(x):

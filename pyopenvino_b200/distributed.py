@@ -42,7 +42,13 @@ def broadcast_weights(flat, src=0):
     """Broadcast the weight arena (one flat tensor, see Executable_Network.load_constants) from `src`;
     afterwards every replica computes with bit-identical weights."""
     if dist.is_initialized() and dist.get_world_size() > 1:
+        if flat.is_cuda:
+            # the arena was filled on the engine's own stream and is read there again right after: order the
+            # collective (queued relative to the CURRENT stream) against both sides with full device syncs
+            torch.cuda.synchronize(flat.device)
         dist.broadcast(flat, src=src)
+        if flat.is_cuda:
+            torch.cuda.synchronize(flat.device)
     return flat
 
 

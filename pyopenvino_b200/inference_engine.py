@@ -240,6 +240,7 @@ class Executable_Network:
         self._plan = None
         self._graph = None
         self._graph_key = None
+        self._captured = {}             # input-dtype signature -> {'graph', 'static_out', 'launches'}
         self._arena = None
         self._static_in = {}
         self._static_out = {}
@@ -272,6 +273,8 @@ class Executable_Network:
             pending = rest
         self._plan = None
         self._graph = None
+        self._graph_key = None
+        self._captured = {}
 
     def prepare_inputs_for_task(self, task) -> dict:
         G = self.ienet.G
@@ -395,10 +398,16 @@ class Executable_Network:
             out_dims = node['output'][common_def.first_output_port(node)]['dims']
             if len(out_dims) != 4:
                 continue
+            # The Concat plugin sees its inputs in G.pred order (= edge insertion order, like the reference's
+            # `inputs.values()`, Concat.py:12); the in-place layout is only right when that IS the IR port order and
+            # every port has its own producer (a producer feeding two ports collapses into one DiGraph edge).
+            conns = [G.edges[(pred, n)]['connection'] for pred in G.pred[n]]
+            ports = [tp for (_fl, _fp, _tl, tp) in conns]
+            if ports != sorted(ports) or len(conns) != len(node['input']):
+                continue                 # fall back to the copying Concat
             slots = {}
             off = 0
-            for pred in G.pred[n]:       # same order the Concat plugin sees its inputs
-                fl, fp, tl, tp = G.edges[(pred, n)]['connection']
+            for fl, fp, tl, tp in conns:
                 c = G.nodes[fl]['output'][fp]['dims'][1]
                 slots[fl] = (off, c)
                 off += c
@@ -551,6 +560,10 @@ class Executable_Network:
         x = self.prepare_inputs_for_task(members[0])[0]
         if not is_device(x) or x.layout != 'nhwc':
             return False
+        # what b200ov_conv2d_multi (f16x2 only) accepts -- otherwise the members run one by one and each picks its own
+        # kernel (conv_f16x2.cu: f16x2_eligible)
+        if x.ptr % 16 != 0 or x.ld % 4 != 0 or x.shape[1] % 8 != 0:
+            return False
         specs, act = [], plan[members[0]]['ops'].get('act')
         for m in members:
             node, st = G.nodes[m], plan[m]
@@ -630,28 +643,56 @@ class Executable_Network:
         return res
 
     # ---- CUDA-graph replay path ----------------------------------------------------------------------
+    # Host inputs keep their native element type across PCIe (uint8 / int8 / float16 / float32, `device.RawInput`) and are
+    # widened by the layout kernel, which is part of the captured launch sequence.  One graph is captured per input-dtype
+    # signature ("key"), lazily; all of them share the arena and the weights.
     def _param_nodes(self):
         G = self.ienet.G
         return [G.nodes[n] for n, _ in self.ienet.find_node_by_type('Parameter')]
 
-    def _prepare_graph(self):
-        """Warm-up (sizes the arena, uploads / packs constants) then capture the launch sequence."""
-        import ctypes as C
+    def _ensure_static_in(self):
+        if not self._static_in:
+            for node in self._param_nodes():
+                shape = tuple(node['data']['shape'])
+                self._static_in[node['name']] = {'node': node, 'shape': shape, 'n': int(np.prod(shape)), 'bufs': {}}
+        return self._static_in
+
+    def _static_buf(self, name, np_dtype):
+        """{'host': pinned tensor, 'dev': RawInput} staging pair of input `name` for element type `np_dtype`."""
         import torch
+        from . import device as dev
+        self._ensure_device()
+        st = self._ensure_static_in()[name]
+        dt = np.dtype(np_dtype)
+        if dt not in st['bufs']:
+            tdt = dev.RawInput.TORCH[dt]
+            st['bufs'][dt] = {'host': dev.pinned_empty(st['n'], tdt),
+                              'dev': dev.RawInput(torch.empty(st['n'], dtype=tdt, device='cuda'), st['shape'], dt)}
+        return st['bufs'][dt]
+
+    def _input_key(self, inputs: dict):
+        """Element type each input crosses PCIe in, e.g. (('data', '|u1'),): selects the captured graph."""
+        from . import device as dev
+        key = []
+        for name in self._ensure_static_in():
+            if inputs is not None and name in inputs:
+                dt = dev.native_input(inputs[name]).dtype
+            elif self._graph_key is not None:
+                dt = np.dtype(dict(self._graph_key)[name])
+            else:
+                dt = np.dtype(np.float32)
+            key.append((name, np.dtype(dt).str))
+        return tuple(key)
+
+    def _prepare_graph(self, key=None):
+        """Warm-up (sizes the arena, uploads / packs constants) then capture the launch sequence for input signature `key`."""
+        import ctypes as C
         from . import _cabi, kernels
         from . import device as dev
-        from .device import DeviceArray
         G = self.ienet.G
         self.load_constants()
-        # static input staging: pinned host + device buffers
-        self._static_in = {}
-        for node in self._param_nodes():
-            shape = tuple(node['data']['shape'])
-            n = int(np.prod(shape))
-            self._static_in[node['name']] = {
-                'host': dev.pinned_empty(n),
-                'dev': DeviceArray(torch.empty(n, dtype=torch.float32, device='cuda'), shape, 'plain'),
-                'node': node}
+        if key is None:
+            key = self._input_key(self._user_inputs)
         # 1) constants: evaluated once, outside the arena, then frozen
         consts = self._mark_constants()
         dev.set_arena(None)
@@ -669,12 +710,15 @@ class Executable_Network:
                     node['output'][port_id]['data'] = data
                 self._plan[task]['const_done'] = True
         # 2) warm-up pass inside the arena (also packs weights: those allocations are persistent)
-        self._arena = dev.Arena()
+        if self._arena is None:
+            self._arena = dev.Arena()
+        self._graph_key = key
         self.stage_inputs(self._user_inputs)
-        for st in self._static_in.values():
-            st['node']['param'] = st['dev']
+        for name, dt in key:
+            self._static_in[name]['node']['param'] = self._static_buf(name, dt)['dev']
         dev.set_arena(self._arena)
         try:
+            self._arena.frozen = False
             self._arena.reset()
             self._static_out = {}
             self._run(capture=True)
@@ -691,106 +735,147 @@ class Executable_Network:
             finally:
                 g = C.c_void_p(0)
                 _cabi.call('b200ov_graph_end', s, C.byref(g))
-            self._graph = g
             self._graph_launches = _cabi.launch_count - launches0
+            self._captured[key] = {'graph': g, 'static_out': self._static_out, 'launches': self._graph_launches}
+            self._graph = g
         finally:
             dev.set_arena(None)
-        self._out_host = {name: dev.pinned_empty(arr.size)
-                          for name, arr in self._static_out.items()}
+        if not getattr(self, '_out_host', None):
+            self._out_host = {name: dev.pinned_empty(arr.size) for name, arr in self._static_out.items()}
+
+    def _select_graph(self, inputs: dict):
+        """Make the graph captured for the dtype signature of `inputs` current (capturing it first if needed)."""
+        key = self._input_key(inputs)
+        if key not in self._captured:
+            self._user_inputs = dict(inputs) if inputs else self._user_inputs
+            self._prepare_graph(key)
+        cap = self._captured[key]
+        self._graph, self._graph_key, self._static_out, self._graph_launches = cap['graph'], key, cap['static_out'], cap['launches']
+        for name, dt in key:
+            self._static_in[name]['node']['param'] = self._static_buf(name, dt)['dev']
+        return key
 
     def stage_inputs(self, inputs: dict = None):
-        """Copy host inputs (default: the arrays given to the last infer()) into the static device buffers."""
-        import torch
-        for name, st in self._static_in.items():
+        """Copy host inputs (default: the arrays given to the last infer()) into the static device buffers of their
+        element type.  An array that already IS the pinned staging buffer (`input_buffer()`) is not copied on the host."""
+        from . import device as dev
+        for name, st in self._ensure_static_in().items():
             val = inputs[name] if inputs is not None and name in inputs else None
             if val is None:
                 continue
-            staging = st['host'].numpy()
-            a = np.asarray(val)
-            if not (a.dtype == np.float32 and a.size == staging.size and a.__array_interface__['data'][0] == staging.__array_interface__['data'][0]):
-                # ordinary (pageable) user array: cast + copy into the pinned staging buffer first
-                a = np.asarray(val, dtype=np.float32).reshape(-1)
-                assert a.size == staging.size, 'input {} has {} elements, network expects {}'.format(name, a.size, staging.size)
-                staging[:] = a
-            st['dev'].t.copy_(st['host'], non_blocking=True)
+            a = dev.native_input(val)
+            buf = self._static_buf(name, a.dtype)
+            staging = buf['host'].numpy()
+            assert a.size == staging.size, 'input {} has {} elements, network expects {}'.format(name, a.size, staging.size)
+            if a.__array_interface__['data'][0] != staging.__array_interface__['data'][0]:
+                staging[:] = a.reshape(-1)             # ordinary (pageable) user array: one host copy into pinned memory
+            buf['dev'].t.copy_(buf['host'], non_blocking=True)
 
-    def input_buffer(self, name: str):
-        """Pinned host ndarray (IR shape, float32) for input `name`.  Filling it in place and passing it to
-        `infer()` skips the pageable->pinned staging copy: the H2D DMA reads it directly."""
-        if not self._static_in:
-            raise RuntimeError('input_buffer() is available after the first infer() in CUDA-graph mode')
-        st = self._static_in[name]
-        return st['host'].numpy().reshape(tuple(st['node']['data']['shape']))
+    def input_buffer(self, name: str, dtype=np.float32):
+        """Pinned host ndarray (IR shape, element type `dtype`: float32 / float16 / uint8 / int8) for input `name`.
+        Filling it in place and passing it to `infer()` skips the pageable->pinned staging copy: the H2D DMA reads it
+        directly."""
+        st = self._ensure_static_in()[name]
+        return self._static_buf(name, dtype)['host'].numpy().reshape(st['shape'])
 
     def replay(self):
-        """Launch the captured graph on self.stream (inputs must already be staged)."""
+        """Launch the current captured graph on self.stream (inputs must already be staged)."""
         import ctypes as C
         from . import _cabi
         _cabi.call('b200ov_graph_launch', self._graph, C.c_void_p(self.stream.cuda_stream))
 
     # ---- asynchronous requests (the reference accepts `num_requests` and ignores it, inference_engine.py:86) ----
-    def start_async(self, inputs: dict) -> int:
-        """Queue one inference and return its request id.  Two request slots: the H2D copy of request i+1 runs
-        on a copy stream while request i computes, so a caller that keeps two requests in flight
-        (start_async(i+1) before wait(i)) hides the PCIe transfer behind the kernels.  `inputs` maps input
-        names to host arrays; `request_buffer(slot, name)` gives the slot's pinned staging array for callers
-        that want to fill it in place."""
+    NUM_REQUESTS = 2
+
+    def _ensure_requests(self):
+        import torch
+        from . import device as dev
+        if not getattr(self, '_requests', None):
+            self._copy_stream = torch.cuda.Stream()
+            self._requests = [{'host': {}, 'dev': {}, 'out_host': {}, 'busy': False, 'inputs': None, 'key': None,
+                               'h2d_done': torch.cuda.Event(), 'done': torch.cuda.Event(),
+                               'status': dev.pinned_empty(1, torch.int32, zero=True)} for _ in range(self.NUM_REQUESTS)]
+            self._next_request = 0
+        return self._requests
+
+    def _request_buf(self, slot, name, np_dtype):
+        import torch
+        from . import device as dev
+        rq = self._ensure_requests()[slot]
+        st = self._ensure_static_in()[name]
+        k = (name, np.dtype(np_dtype).str)
+        if k not in rq['host']:
+            tdt = dev.RawInput.TORCH[np.dtype(np_dtype)]
+            rq['host'][k] = dev.pinned_empty(st['n'], tdt)
+            rq['dev'][k] = torch.empty(st['n'], dtype=tdt, device='cuda')
+        return rq['host'][k], rq['dev'][k]
+
+    def next_slot(self) -> int:
+        """The request slot the next `start_async(inputs)` (without an explicit `slot`) will use."""
+        self._ensure_device()
+        self._ensure_requests()
+        return self._next_request
+
+    def request_buffer(self, slot: int, name: str, dtype=np.float32):
+        """Pinned host ndarray (IR shape, element type `dtype`) owned by request slot `slot` for input `name`.  Fill it
+        and pass it to `start_async(..., slot=slot)`: the H2D DMA then reads it in place (no host copy)."""
+        self._ensure_device()
+        st = self._ensure_static_in()[name]
+        return self._request_buf(slot, name, dtype)[0].numpy().reshape(st['shape'])
+
+    def start_async(self, inputs: dict, slot: int = None) -> int:
+        """Queue one inference and return its request slot.  NUM_REQUESTS slots: the H2D copy of one request runs on a
+        copy stream while the previous one computes, so a caller that keeps two requests in flight (start_async(i+1)
+        before wait(i)) hides the PCIe transfer behind the kernels.  `inputs` maps input names to host arrays in their
+        native element type.  `slot` pins the request to a slot (default: round robin, see `next_slot()`); an input
+        that is the slot's own `request_buffer(slot, name, dtype)` is transferred without a host copy, any other array
+        is first copied into it."""
         import torch
         from . import kernels
         from . import device as dev
         self._ensure_device()
-        if self._graph is None:
-            self.infer(inputs)                     # builds the plan, warms up, captures the graph
-        if not getattr(self, '_requests', None):
-            self._copy_stream = torch.cuda.Stream()
-            self._requests = []
-            for _ in range(2):
-                rq = {'host': {}, 'dev': {}, 'out_host': {}, 'busy': False, 'inputs': None,
-                      'h2d_done': torch.cuda.Event(), 'done': torch.cuda.Event(),
-                      'status': dev.pinned_empty(1, torch.int32, zero=True)}
-                for name, st in self._static_in.items():
-                    rq['host'][name] = dev.pinned_empty(st['host'].numel())
-                    rq['dev'][name] = torch.empty_like(st['dev'].t)
-                for name, arr in self._static_out.items():
-                    rq['out_host'][name] = dev.pinned_empty(arr.size)
-                self._requests.append(rq)
-            self._next_request = 0
-        slot = self._next_request
-        self._next_request ^= 1
+        if self._plan is None:
+            self.build_plan()
+        self._ensure_requests()
+        with torch.cuda.stream(self.stream):
+            key = self._select_graph(inputs)
+        cap = self._captured[key]
+        if slot is None:
+            slot = self._next_request
+        assert 0 <= slot < self.NUM_REQUESTS
+        self._next_request = (slot + 1) % self.NUM_REQUESTS
         rq = self._requests[slot]
         if rq['busy']:
             rq['done'].synchronize()               # the slot's previous request must have drained
-        rq['inputs'] = dict(inputs)
+        rq['inputs'], rq['key'] = dict(inputs), key
+        for name, arr in cap['static_out'].items():
+            if name not in rq['out_host']:
+                rq['out_host'][name] = dev.pinned_empty(arr.size)
         with torch.cuda.stream(self._copy_stream):
-            for name, st in self._static_in.items():
+            for name, dt in key:
                 if name not in inputs:
                     continue
-                staging = rq['host'][name].numpy()
-                a = np.asarray(inputs[name])
-                if not (a.dtype == np.float32 and a.size == staging.size and
-                        a.__array_interface__['data'][0] == staging.__array_interface__['data'][0]):
-                    a = np.asarray(inputs[name], dtype=np.float32).reshape(-1)
-                    assert a.size == staging.size, 'input {} has {} elements, network expects {}'.format(name, a.size, staging.size)
-                    staging[:] = a
-                rq['dev'][name].copy_(rq['host'][name], non_blocking=True)
+                host, devbuf = self._request_buf(slot, name, dt)
+                staging = host.numpy()
+                a = dev.native_input(inputs[name])
+                assert a.size == staging.size, 'input {} has {} elements, network expects {}'.format(name, a.size, staging.size)
+                if a.__array_interface__['data'][0] != staging.__array_interface__['data'][0]:
+                    staging[:] = a.reshape(-1)
+                devbuf.copy_(host, non_blocking=True)
             rq['h2d_done'].record(self._copy_stream)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(rq['h2d_done'])
             kernels.status_reset()
-            for name, st in self._static_in.items():
-                st['dev'].t.copy_(rq['dev'][name], non_blocking=True)          # D2D into the graph's input buffer
+            for name, dt in key:
+                if name in inputs:                     # D2D into the graph's input buffer
+                    self._static_buf(name, dt)['dev'].t.copy_(self._request_buf(slot, name, dt)[1], non_blocking=True)
             self.replay()
-            for name, arr in self._static_out.items():
+            for name, arr in cap['static_out'].items():
                 rq['out_host'][name][:arr.size].copy_(arr.t[:arr.size], non_blocking=True)
             kernels.status_fetch(rq['status'])
             rq['done'].record(self.stream)
         rq['busy'] = True
         return slot
-
-    def request_buffer(self, slot: int, name: str):
-        """Pinned host ndarray (IR shape) of request slot `slot` for input `name` (available after the first start_async)."""
-        st = self._static_in[name]
-        return self._requests[slot]['host'][name].numpy().reshape(tuple(st['node']['data']['shape']))
 
     def wait(self, slot: int) -> dict:
         """Block until request `slot` has finished and return {result_name: ndarray}."""
@@ -801,7 +886,8 @@ class Executable_Network:
             import torch
             with torch.cuda.stream(self.stream):
                 return self._infer_full_range(rq['inputs'])
-        return {name: rq['out_host'][name][:arr.size].numpy().reshape(arr.shape).copy() for name, arr in self._static_out.items()}
+        outs = self._captured[rq['key']]['static_out']
+        return {name: rq['out_host'][name][:arr.size].numpy().reshape(arr.shape).copy() for name, arr in outs.items()}
 
     def _infer_full_range(self, inputs: dict, verbose: bool = False):
         """The f16x2 contractions saw a non-finite output: an operand left the FP16 range (|v| > 65504) or the
@@ -842,8 +928,7 @@ class Executable_Network:
         return res
 
     def _infer_graph(self):
-        if self._graph is None:
-            self._prepare_graph()
+        self._select_graph(self._user_inputs)
         self.stage_inputs(self._user_inputs)
         self.replay()
         return self.fetch_outputs()
@@ -882,6 +967,27 @@ class Executable_Network:
         self._weights = flat
         return flat
 
+    def broadcast_constants(self, src: int = 0):
+        """Multi-GPU load step: make rank `src`'s weight arena the replica every rank computes with.
+        Synchronises both sides of the NCCL broadcast and rebuilds everything derived from the constants on this
+        rank -- the small host mirrors and the packed / split weight forms -- so nothing stale survives when the
+        ranks did not load identical `.bin` files.  Must run before the first inference."""
+        from . import distributed
+        flat = self.load_constants()
+        rank, size, _ = distributed.world()
+        distributed.broadcast_weights(flat, src=src)
+        if size > 1 and rank != src:
+            G = self.ienet.G
+            for node_id, _name in self.ienet.find_node_by_type('Const'):
+                arr = G.nodes[node_id]['const'].get('device')
+                if arr is None:
+                    continue
+                had_host = 'host' in arr.cache
+                arr.cache.clear()
+                if had_host:
+                    arr.cache['host'] = arr.numpy()
+        return flat
+
     def profile_steps(self, inputs: dict, iters: int = 3):
         """Per-step device time of the fused plan run eagerly (CUDA events around every plugin call on
         self.stream).  Returns [{'id', 'type', 'name', 'ms'}] averaged over `iters` passes."""
@@ -895,14 +1001,14 @@ class Executable_Network:
         acc = {}
         with torch.cuda.stream(self.stream):
             if self.use_graph:
-                if self._graph is None:
-                    self._prepare_graph()
+                self._select_graph(inputs)
                 self.stage_inputs(inputs)
             else:
                 for name, val in inputs.items():
                     for node in G.nodes:
                         if G.nodes[node]['name'] == name:
                             G.nodes[node]['param'] = val
+            self.load_constants()        # weights must never come out of the per-inference arena
             arena = self._arena if self._arena is not None else dev.Arena()
             frozen = arena.frozen
             arena.frozen = False

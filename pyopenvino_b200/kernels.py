@@ -107,6 +107,33 @@ def to_nhwc(x, scale=None, shift=None, out=None):
     return out
 
 
+def input_to_device(raw, scale=None, shift=None, nhwc=True):
+    """RawInput (native element type, IR layout) -> float32 DeviceArray: NHWC (+ folded scale / shift) for 4-D inputs
+    when `nhwc`, else a plain widened copy.  One kernel; the widening is exact."""
+    if raw.ndim == 4 and nhwc:
+        n, c, h, w = raw.shape
+        ld = 4 if c == 3 else c
+        out = DeviceArray(dev.alloc_f32(n * h * w * ld), raw.shape, 'nhwc', ld=ld)
+        sv, ss, hs = _affine_operand(scale, c)
+        bv, bs, hb = _affine_operand(shift, c)
+        _cabi.call('b200ov_input_to_nhwc', C.c_void_p(raw.ptr), raw.code, _p(out), n, c, h * w, out.ld, hs, sv, ss, hb, bv, bs, _s())
+        return out
+    assert scale is None and shift is None
+    out = DeviceArray(dev.alloc_f32(raw.size), raw.shape, 'plain')
+    _cabi.call('b200ov_widen', C.c_void_p(raw.ptr), raw.code, _p(out), raw.size, _s())
+    return out
+
+
+def upload_raw(arr):
+    """Host ndarray of a native input type -> RawInput (one H2D copy of arr.nbytes on the current stream)."""
+    dev.init()
+    a = np.ascontiguousarray(dev.native_input(arr))
+    t = torch.empty(max(a.size, 1), dtype=dev.RawInput.TORCH[a.dtype], device='cuda')
+    if a.size:
+        t[:a.size].copy_(torch.from_numpy(a.reshape(-1)), non_blocking=False)
+    return dev.RawInput(t, a.shape, a.dtype)
+
+
 def to_plain(x):
     """NHWC -> plain NCHW (the layout a host consumer or a flattening Reshape needs)."""
     assert x.layout == 'nhwc'

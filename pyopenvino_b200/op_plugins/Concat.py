@@ -1,5 +1,6 @@
-"""Concat plugin -- drop-in for `op_plugins/Concat.py` (`np.concatenate` along `axis`, inputs in port
-order, `Concat.py:9-13`).
+"""Concat plugin -- drop-in for `op_plugins/Concat.py` (`np.concatenate` along `axis` over
+`inputs.values()`, i.e. in the order the executor filled the dict = edge order of the IR, which is port order in
+every shipped model but is not sorted by port -- exactly like the reference, `Concat.py:9-13`).
 
 On the device a channel concat of NHWC feature maps is a set of strided row copies
 (`b200ov_copy2d`) -- or nothing at all when the executor already made the producers write into

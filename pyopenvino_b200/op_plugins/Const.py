@@ -25,6 +25,12 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
             const['host'] = np.array(const['data'], dtype=precision).reshape(shape)
         return {0: const['host']}
     if 'device' not in const:
+        from .. import device as dev
         host = np.array(const['data'], dtype=precision).reshape(shape)
-        const['device'] = kernels.upload(host, keep_host=host.size <= 4096)
+        arena = dev.current_arena()
+        dev.set_arena(None)              # resident for the life of the network: never from the per-inference arena
+        try:
+            const['device'] = kernels.upload(host, keep_host=host.size <= 4096)
+        finally:
+            dev.set_arena(arena)
     return {0: const['device']}

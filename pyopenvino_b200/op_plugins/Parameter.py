@@ -8,7 +8,7 @@ conversion kernel through `fused`.
 import numpy as np
 
 from .. import common_def, kernels
-from ..device import is_device
+from ..device import DeviceArray, RawInput, is_device, native_input
 
 
 def name():
@@ -21,12 +21,21 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
     shape = node['data']['shape']
     precision = common_def.type_convert_tbl[node['data']['element_type']]
     param = node['param']
+    f = fused or {}
+    to_nhwc = f.get('scale') is not None or f.get('shift') is not None or f.get('to_nhwc')
     if is_device(param):                      # executor staged the batch in a static device buffer already
         assert tuple(param.shape) == tuple(shape)
         x = param
+    elif isinstance(param, RawInput) or precision is np.float32:
+        # the input crosses PCIe in its native width (uint8 / int8 / float16 / float32); the cast to the IR precision
+        # (`.astype(precision)`, Parameter.py:13) happens in the layout kernel and is exact for these types
+        raw = param if isinstance(param, RawInput) else kernels.upload_raw(np.asarray(native_input(param)).reshape(shape))
+        assert tuple(raw.shape) == tuple(shape)
+        if raw.np_dtype == np.float32 and not (raw.ndim == 4 and to_nhwc):
+            return {0: DeviceArray(raw.t, raw.shape, 'plain')}
+        return {0: kernels.input_to_device(raw, scale=f.get('scale'), shift=f.get('shift'), nhwc=bool(to_nhwc))}
     else:
         x = kernels.upload(np.array(param).reshape(shape).astype(precision))
-    f = fused or {}
-    if x.ndim == 4 and (f.get('scale') is not None or f.get('shift') is not None or f.get('to_nhwc')):
+    if x.ndim == 4 and to_nhwc:
         x = kernels.to_nhwc(x, scale=f.get('scale'), shift=f.get('shift'))
     return {0: x}

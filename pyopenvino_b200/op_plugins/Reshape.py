@@ -36,6 +36,10 @@ def resolve_shape(in_shape, target):
                 size //= d
     if deferred != -1:
         dims[deferred] = int(size)
+    elif size != 1:
+        # the reference's `input0.reshape(adjusted_dims)` raises here (`Reshape.py:44`): a target without -1 must keep
+        # the element count (e.g. a hard-coded batch-1 target on a re-batched network)
+        raise ValueError('cannot reshape array of shape {} into shape {}'.format(tuple(in_shape), tuple(dims)))
     return tuple(dims)
 
 

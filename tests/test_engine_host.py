@@ -146,6 +146,13 @@ def test_shape_rules_match_oracle():
     assert resolve_shape((2, 3, 3, 12), [0, -1, 1, 4]) == (2, 27, 1, 4)
     with pytest.raises(AssertionError):
         resolve_shape((2, 3), [-1, -1])
+    # a target without -1 must keep the element count (the reference's ndarray.reshape raises, Reshape.py:44):
+    # a hard-coded batch-1 target on a re-batched network must not silently drop images
+    with pytest.raises(ValueError):
+        resolve_shape((4, 3, 3, 64), [1, 576])
+    with pytest.raises(ValueError):
+        np.zeros((4, 3, 3, 64)).reshape((1, 576))
+    assert resolve_shape((4, 3, 3, 64), [4, 576]) == (4, 576)
 
 
 def test_no_product_module_imports_the_oracle():
