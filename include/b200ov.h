@@ -131,6 +131,15 @@ int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_p
                   const float* bias, int act, float act_lo, float act_hi, int math,
                   float* y, int ldy, void* stream);
 
+/* Split-K form for products with few output tiles (6272 -> 512 at batch 1024 is 32 tiles on 148 SMs): several CTAs share
+ * one output tile, each over a slice of K, writing raw partial sums to `workspace`; a second kernel adds them in split
+ * order (deterministic), then bias and activation.  b200ov_matmul_workspace() returns the bytes b200ov_matmul_ws() wants
+ * for this shape (0: no split, plain b200ov_matmul behaviour; a NULL workspace is always accepted).  MatMul.py:9-17. */
+int b200ov_matmul_workspace(int m, int n, int k, size_t* bytes);
+int b200ov_matmul_ws(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw,
+                     const float* bias, int act, float act_lo, float act_hi, int math,
+                     float* y, int ldy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device address of the library's sticky status word (uint32).  Bit 0 is set by a B200OV_MATH_F16X2
  * contraction whose output held a non-finite value (an operand beyond the FP16 range, or inf/NaN data).
  * The executor clears it before an inference (cudaMemsetAsync), reads it back with the results and, if set,

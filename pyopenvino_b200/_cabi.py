@@ -76,6 +76,8 @@ SIGNATURES = {
     'b200ov_conv2d': [C.POINTER(ConvDesc), _P, _P, _P, _P, _P],
     'b200ov_conv2d_multi': [C.POINTER(ConvDesc), _P, _P, _P, _I, C.POINTER(ConvSeg), _P],
     'b200ov_matmul': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P],
+    'b200ov_matmul_workspace': [_I, _I, _I, C.POINTER(_Z)],
+    'b200ov_matmul_ws': [_I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _F, _I, _P, _I, _P, _Z, _P],
     'b200ov_status_word': [C.POINTER(C.c_void_p)],
     'b200ov_status_reset': [_P],
     'b200ov_status_fetch': [_P, _P],
@@ -98,7 +100,7 @@ NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
 _lib = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
-_LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
+_LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_matmul_ws', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
               'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_transpose',
               'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_detection_output'}
 

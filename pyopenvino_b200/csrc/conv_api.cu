@@ -10,7 +10,10 @@ int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, c
 bool f16x2_eligible(const b200ov_conv_desc* d, const float* x);
 int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s);
 int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
-                       const b200ov_conv_seg* segs, cudaStream_t s);
+                       const b200ov_conv_seg* segs, cudaStream_t s, int ksplit, int ws_rows);
+int f16x2_splitk_plan(int m, int cout, int cin, int kh, int kw, int* ws_rows, int* ws_ld);
+int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, float* ws,
+                        size_t ws_bytes, cudaStream_t s);
 unsigned int* f16x2_status_word();
 bool has_tf32_section(int cin);
 void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* kpad);
@@ -88,11 +91,27 @@ int b200ov_conv2d_multi(const b200ov_conv_desc* d, const float* x, const float* 
   B200OV_REQUIRE(d->act >= B200OV_ACT_NONE && d->act <= B200OV_ACT_CLAMP, "conv2d_multi: bad activation");
   if (d->math != B200OV_MATH_AUTO && d->math != B200OV_MATH_F16X2)
     return set_error(B200OV_ERR_UNSUPPORTED, "conv2d_multi: only the f16x2 path supports several output tensors");
-  return conv2d_f16x2_multi(d, x, f16_section(d, w_packed), bias, nseg, segs, as_stream(stream));
+  return conv2d_f16x2_multi(d, x, f16_section(d, w_packed), bias, nseg, segs, as_stream(stream), 1, 0);
 }
 
 int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw, const float* bias,
                   int act, float act_lo, float act_hi, int math, float* y, int ldy, void* stream) {
+  return b200ov_matmul_ws(m, n, k, a, lda, b_packed, ldw, bias, act, act_lo, act_hi, math, y, ldy, nullptr, 0, stream);
+}
+
+int b200ov_matmul_workspace(int m, int n, int k, size_t* bytes) {
+  B200OV_REQUIRE(bytes && m >= 0 && n > 0 && k > 0, "matmul_workspace: bad argument");
+  *bytes = 0;
+  if (m == 0 || k % 8 != 0) return B200OV_OK;
+  int ws_rows, ws_ld;
+  const int ksplit = f16x2_splitk_plan(m, n, k, 1, 1, &ws_rows, &ws_ld);
+  if (ksplit > 1) *bytes = (size_t)ksplit * ws_rows * ws_ld * sizeof(float);
+  return B200OV_OK;
+}
+
+int b200ov_matmul_ws(int m, int n, int k, const float* a, int lda, const float* b_packed, int ldw, const float* bias,
+                     int act, float act_lo, float act_hi, int math, float* y, int ldy, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   B200OV_REQUIRE(m >= 0 && n > 0 && k > 0, "matmul: bad dims");
   b200ov_conv_desc d;
   memset(&d, 0, sizeof(d));
@@ -101,6 +120,13 @@ int b200ov_matmul(int m, int n, int k, const float* a, int lda, const float* b_p
   d.pt = 0; d.pl = 0; d.oh = 1; d.ow = m > 0 ? m : 1; d.x_ld = lda; d.y_ld = ldy; d.ldw = ldw;
   d.act = act; d.act_lo = act_lo; d.act_hi = act_hi; d.math = math;
   if (m == 0) return B200OV_OK;
+  if (workspace != nullptr && workspace_bytes > 0 && (math == B200OV_MATH_AUTO || math == B200OV_MATH_F16X2) && f16x2_eligible(&d, a) &&
+      act != B200OV_ACT_SIGMOID) {
+    int rc = validate(&d, a, b_packed, y);
+    if (rc) return rc;
+    return conv2d_f16x2_splitk(&d, a, f16_section(&d, b_packed), bias, y, static_cast<float*>(workspace), workspace_bytes,
+                               as_stream(stream));
+  }
   return b200ov_conv2d(&d, a, b_packed, bias, y, stream);
 }
 

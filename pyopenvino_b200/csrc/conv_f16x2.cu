@@ -105,8 +105,19 @@ struct Params {
   int wide_loads;                      // 1: 256-bit gathers (x 32-byte aligned, x_ld % 8 == 0)
   int pair4;                           // 1: cin <= 4 with a pixel pitch of 4 floats: a unit is two horizontally
                                        //    adjacent filter taps x 4 channels (d_upt then divides by units per filter ROW)
-  FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots;
+  // split-K (MatMul with few output tiles): tile index = (m_blk * tiles_n + n_blk) * ksplit + ks; split ks covers slots
+  // [ks * num_slots, (ks + 1) * num_slots) of the K range (num_slots = slots per split, even) and writes its raw partial
+  // sums to rows [ks * ws_rows + m, ...) of the workspace, which a second kernel reduces in a fixed order.
+  int ksplit, ws_rows;
+  FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots, d_ksplit;
 };
+
+// tile index -> (row block, column block, K split)
+__device__ __forceinline__ void tile_coord(const Params& p, uint32_t tile, uint32_t& m_blk, uint32_t& n_blk, uint32_t& ks) {
+  uint32_t q;
+  p.d_ksplit.divmod(tile, q, ks);
+  p.d_tiles_n.divmod(q, m_blk, n_blk);
+}
 
 __device__ __align__(32) float g_zero_run[8];      // source of the np.pad zeros
 
@@ -301,8 +312,11 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
         uint32_t bcount = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
           const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
-          const int n0 = (int)(tile - p.d_tiles_n.div(tile) * p.d_tiles_n.d) * BLOCK_N;
-          for (int ks = 0; ks < num_stages; ++ks, ++bcount) {
+          uint32_t m_blk_, n_blk_, ksp_;
+          tile_coord(p, tile, m_blk_, n_blk_, ksp_);
+          const int n0 = (int)n_blk_ * BLOCK_N;
+          const int stage0 = (int)ksp_ * num_stages;
+          for (int ks = stage0; ks < stage0 + num_stages; ++ks, ++bcount) {
             const int s = bcount % SB;
             F16_WAIT(0, bar_b_empty(s), ((bcount / SB) & 1) ^ 1);
             if (elect_one_sync()) {
@@ -430,7 +444,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     // row state of the tile the gather is currently in: rows 32q + 16g + rsub + 8h  (r = 2g + h)
     const float* rbase[4];
     int riy[4], rix[4];
-    uint32_t cur_tl = 0xffffffffu;
+    uint32_t cur_tl = 0xffffffffu, cur_slot0 = 0;
     F16_TRACE_DECL
     auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
       uint32_t tl, slot;
@@ -438,7 +452,10 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       if (tl != cur_tl) {
         cur_tl = tl;
         const uint32_t tile = blockIdx.x + tl * gridDim.x;
-        const int m0 = (int)p.d_tiles_n.div(tile) * BLOCK_M;
+        uint32_t m_blk_, n_blk_, ksp_;
+        tile_coord(p, tile, m_blk_, n_blk_, ksp_);
+        cur_slot0 = ksp_ * (uint32_t)p.num_slots;
+        const int m0 = (int)m_blk_ * BLOCK_M;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int m = m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
@@ -450,7 +467,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           rbase[r] = x + ((long long)((int)img * p.h + riy[r]) * p.w + rix[r]) * p.x_ld;
         }
       }
-      const uint32_t unit = slot * 4 + u4;
+      const uint32_t unit = (cur_slot0 + slot) * 4 + u4;
       const bool uvalid = unit < (uint32_t)p.units;
       if constexpr (!PAIR) {
         uint32_t tap, cu, ky, kx;
@@ -535,9 +552,10 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     F16_TRACE_DECL
     for (int tl = 0; tl < my_tiles; ++tl) {
       const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
-      uint32_t m_blk, n_blk;
-      p.d_tiles_n.divmod(tile, m_blk, n_blk);
+      uint32_t m_blk, n_blk, ksp;
+      tile_coord(p, tile, m_blk, n_blk, ksp);
       const int m0 = (int)m_blk * BLOCK_M, n0 = (int)n_blk * BLOCK_N;
+      const int row_off = (int)ksp * p.ws_rows;                 // split-K: this split's block of workspace rows
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);                 // everyone is done with the previous tile's bias
       if (e < BLOCK_N) sbias[e] = (bias != nullptr && n0 + e < p.cout) ? __ldg(bias + n0 + e) : 0.f;
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);
@@ -627,7 +645,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
               const int sg = segment_of(n0 + (round * L::STG_BLOCKS + sb) * 32, local);
               if (sg >= 0 && m0 + 32 * q < p.M) {
                 const CUtensorMap* mp = sg == 0 ? &map_y0 : (sg == 1 ? &map_y1 : &map_y2);
-                tma_store_2d(mp, stage_u32 + sb * 4096, local, m0 + 32 * q);
+                tma_store_2d(mp, stage_u32 + sb * 4096, local, row_off + m0 + 32 * q);
               }
             }
             tma_store_commit();
@@ -646,7 +664,7 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
             for (int r = 0; r < 32; ++r) {
               const int m = m0 + 32 * q + r;
               const float v = *reinterpret_cast<const float*>(stage_ptr + sb * 4096 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-              if (m < p.M && n < ncout) ys[(long long)m * yld + n] = v;
+              if (m < p.M && n < ncout) ys[(long long)(row_off + m) * yld + n] = v;
             }
           }
           __syncwarp();
@@ -807,8 +825,32 @@ unsigned int* f16x2_status_word() {
 
 // `wt` points at the f16 section of the packed weights: [hi plane | lo plane] of halfs.  d->cout is the width of the
 // (fused) weight matrix; the output columns are routed to `nseg` tensors.
+// Split-K plan for a contraction with too few output tiles to fill the GPU (MatMul: 6272 -> 512 at batch 1024 is 32
+// tiles on 148 SMs, and every tile walks all 196 K slots): ksplit CTAs share one output tile, each over 1/ksplit of K.
+// Returns ksplit (1 = do not split) and the workspace geometry [ksplit * ws_rows][ws_ld] floats.
+int f16x2_splitk_plan(int m, int cout, int cin, int kh, int kw, int* ws_rows, int* ws_ld) {
+  int coutp, kpad, upt, units;
+  f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, &upt, &units);
+  const int num_slots = ceil_div(units, 4);
+  int block_n = cout > 64 ? 128 : (cout > 32 ? 64 : 32);
+  if (cout > 64 && ceil_div(cout, 96) == ceil_div(cout, 128)) block_n = 96;
+  const long long tiles = (long long)ceil_div(m, f16::BLOCK_M) * ceil_div(cout, block_n);
+  const int sms = props().sm_count > 0 ? props().sm_count : 148;
+  int ksplit = 1;
+  if (tiles * 2 <= sms && num_slots >= 16) {
+    ksplit = (int)(sms / tiles);
+    if (ksplit > num_slots / 8) ksplit = num_slots / 8;          // at least 8 slots (256 K elements) per split
+    if (ksplit > 16) ksplit = 16;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (const char* e = getenv("B200OV_F16_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 32) ksplit = v; }   // developer knob
+  if (ws_rows) *ws_rows = round_up(m, f16::BLOCK_M);
+  if (ws_ld) *ws_ld = round_up(cout, 4);
+  return ksplit;
+}
+
 int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
-                       const b200ov_conv_seg* segs, cudaStream_t s) {
+                       const b200ov_conv_seg* segs, cudaStream_t s, int ksplit, int ws_rows) {
   if (!f16x2_eligible(d, x))
     return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with cin %% 8 == 0 (or cin <= 4 at a pixel pitch of 4) and no fused Sigmoid");
   if (nseg < 1 || nseg > 3) return set_error(B200OV_ERR_INVALID, "conv2d: 1..3 output segments");
@@ -833,6 +875,13 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
   p.units = units;
   p.num_slots = ceil_div(units, 4);
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > 1) {
+    if (nseg != 1 || bias != nullptr || d->act != B200OV_ACT_NONE || ws_rows < (int)M)
+      return set_error(B200OV_ERR_INVALID, "conv2d: split-K writes raw partial sums of one tensor (no bias / activation)");
+    p.num_slots = round_up(ceil_div(p.num_slots, ksplit), 2);     // whole weight stages; the last split's tail reads zeros
+  }
+  p.ksplit = ksplit; p.ws_rows = ksplit > 1 ? ws_rows : 0;
   // Tile width: 128 columns, or 96 where that needs no more tiles (C_out in (64, 96], (128, 192], (256, 288]): an
   // N = 96 MMA takes 56 cycles against 64 for N = 128 (tools/ubench/mma_rate.cu), a 96-wide tile leaves TMEM room
   // for a second cross-term accumulator, and e.g. C_out = 192 is two full tiles instead of one and a half.
@@ -843,7 +892,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
     if (v == 32 || v == 64 || v == 96 || v == 128) block_n = v;
   }
   p.tiles_n = ceil_div(d->cout, block_n);
-  const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n;
+  const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n * ksplit;
   if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
   p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
@@ -869,7 +918,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
   p.wide_loads = !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
-  p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots);
+  p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots); p.d_ksplit = FastDiv(ksplit);
   const __half* lo_plane = hi_plane + (long long)coutp * kpad;
   CUtensorMap mh, ml, my[3];
   int rc = f16::make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
@@ -878,7 +927,8 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   if (rc) return rc;
   for (int i = 0; i < 3; ++i) {
     if (p.tma_store && i < nseg) {
-      rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, segs[i].cout, p.M, (long long)segs[i].y_ld * 4, 32, 32);
+      rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, segs[i].cout,
+                            ksplit > 1 ? (long long)ksplit * ws_rows : (long long)p.M, (long long)segs[i].y_ld * 4, 32, 32);
       if (rc) return rc;
     } else {
       my[i] = mh;    // never dereferenced
@@ -899,7 +949,58 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
 int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
   b200ov_conv_seg seg;
   seg.y = y; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = d->y_ld;
-  return conv2d_f16x2_multi(d, x, wt, bias, 1, &seg, s);
+  return conv2d_f16x2_multi(d, x, wt, bias, 1, &seg, s, 1, 0);
+}
+
+// ---- split-K: partial sums -> y = act(bias + sum over splits, in split order) -------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                            float* __restrict__ y, int m, int n, int ws_rows, int ws_ld, int ldy,
+                                                            int ksplit, int act, float lo, float hi) {
+  const int ng = n / V;
+  const long long total = (long long)m * ng;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ng), c0 = (int)(idx - (long long)row * ng) * V;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = bias != nullptr ? __ldg(bias + c0 + j) : 0.f;
+    for (int k = 0; k < ksplit; ++k) {
+      const float* src = ws + ((long long)k * ws_rows + row) * ws_ld + c0;
+      if constexpr (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        acc[0] = __fadd_rn(acc[0], t.x); acc[1] = __fadd_rn(acc[1], t.y); acc[2] = __fadd_rn(acc[2], t.z); acc[3] = __fadd_rn(acc[3], t.w);
+      } else {
+        acc[0] = __fadd_rn(acc[0], __ldg(src));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) y[(long long)row * ldy + c0 + j] = apply_act(acc[j], act, lo, hi);
+  }
+}
+
+int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, float* ws,
+                        size_t ws_bytes, cudaStream_t s) {
+  int ws_rows, ws_ld;
+  const long long M = (long long)d->n * d->oh * d->ow;
+  const int ksplit = f16x2_splitk_plan((int)M, d->cout, d->cin, d->kh, d->kw, &ws_rows, &ws_ld);
+  if (ksplit <= 1 || ws == nullptr) return conv2d_f16x2(d, x, wt, bias, y, s);
+  if (ws_bytes < (size_t)ksplit * ws_rows * ws_ld * sizeof(float) || !aligned16(ws))
+    return set_error(B200OV_ERR_INVALID, "split-K workspace too small or misaligned (%zu bytes)", ws_bytes);
+  b200ov_conv_desc dd = *d;
+  dd.act = B200OV_ACT_NONE;
+  b200ov_conv_seg seg;
+  seg.y = ws; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = ws_ld;
+  int rc = conv2d_f16x2_multi(&dd, x, wt, nullptr, 1, &seg, s, ksplit, ws_rows);
+  if (rc) return rc;
+  const bool vec = d->cout % 4 == 0 && d->y_ld % 4 == 0 && aligned16(y) && (bias == nullptr || aligned16(bias));
+  if (vec)
+    splitk_reduce_kernel<4><<<bw_grid(M * (d->cout / 4), 256), 256, 0, s>>>(ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit,
+                                                                         d->act, d->act_lo, d->act_hi);
+  else
+    splitk_reduce_kernel<1><<<bw_grid(M * d->cout, 256), 256, 0, s>>>(ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit, d->act,
+                                                                   d->act_lo, d->act_hi);
+  B200OV_LAUNCH_CHECK("splitk_reduce_kernel");
+  return B200OV_OK;
 }
 
 }  // namespace b200ov

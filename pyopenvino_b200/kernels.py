@@ -310,8 +310,18 @@ def matmul(a, b, transpose_a=False, transpose_b=True, bias=None, act=None, math=
     out = DeviceArray(dev.alloc_f32(m * n), (m, n), 'plain')
     code, lo, hi = _act(act)
     bv = _vec_ptr(bias, n)
-    _cabi.call('b200ov_matmul', m, n, k, _p(a), k, C.c_void_p(pk.ptr), pk.ldw, _p(bv), code, lo, hi,
-               default_math if math is None else math, _p(out), n, _s())
+    mode = default_math if math is None else math
+    need = C.c_size_t(0)
+    if mode in (_cabi.MATH_AUTO, _cabi.MATH_F16X2):
+        _cabi.call('b200ov_matmul_workspace', m, n, k, C.byref(need))
+    if need.value:
+        # few output tiles: split-K over a workspace of partial sums (from the arena, like every per-inference buffer)
+        ws = dev.alloc_f32(need.value // 4)
+        _cabi.call('b200ov_matmul_ws', m, n, k, _p(a), k, C.c_void_p(pk.ptr), pk.ldw, _p(bv), code, lo, hi, mode, _p(out), n,
+                   C.c_void_p(ws.data_ptr()), need, _s())
+        _cabi.launch_count += 1          # two kernels: the contraction and the reduction
+    else:
+        _cabi.call('b200ov_matmul', m, n, k, _p(a), k, C.c_void_p(pk.ptr), pk.ldw, _p(bv), code, lo, hi, mode, _p(out), n, _s())
     return out
 
 

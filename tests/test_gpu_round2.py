@@ -286,3 +286,39 @@ def test_integration_option_b_maxpool_ctypes_only(tmp_path, shape, kernel, strid
     data = {'kernel': kernel, 'strides': strides, 'pads_begin': pb, 'pads_end': pe, 'rounding_type': rounding, 'auto_pad': 'explicit'}
     want = ref_ops.maxpool(data, x)
     assert np.array_equal(np.load(yout), want)
+
+
+# ---- split-K MatMul ----------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('m,k,n,act', [(1024, 6272, 512, 'relu'), (256, 1024, 1000, None), (1, 576, 64, 'relu'), (64, 6272, 512, None),
+                                       (130, 1000, 10, None), (5, 4104, 36, 'relu')])
+def test_matmul_split_k_vs_oracle(m, k, n, act):
+    """Few output tiles -> several CTAs per tile over slices of K + a fixed-order reduction (bias and activation applied
+    there).  Same tolerance class as the unsplit contraction, deterministic, and K tails that are not whole slots."""
+    import ctypes as C
+    from oracle import ref_ops
+    from pyopenvino_b200 import _cabi, kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(m + k + n)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = (rng.standard_normal((n, k)) * np.sqrt(2.0 / k)).astype(np.float32)
+    bias = (0.05 * rng.standard_normal((1, n))).astype(np.float32)
+    need = C.c_size_t(0)
+    _cabi.call('b200ov_matmul_workspace', m, n, k, C.byref(need))
+    if (m, k, n) in ((1024, 6272, 512), (256, 1024, 1000), (64, 6272, 512)):
+        assert need.value > 0, 'expected a split-K plan for this shape'
+    da, db, dbias = kernels.upload(a), kernels.upload(b), kernels.upload(bias)
+    fact = ('relu',) if act else None
+    got = np.asarray(kernels.matmul(da, db, bias=dbias, act=fact))
+    want = ref_ops.add(ref_ops.matmul({'transpose_a': 'false', 'transpose_b': 'true'}, a, b), bias)
+    if act:
+        want = ref_ops.relu(want)
+    ok, msg = close(got, want)
+    assert ok, msg
+    for _ in range(3):
+        assert np.array_equal(np.asarray(kernels.matmul(da, db, bias=dbias, act=fact)), got)
+    # the unsplit kernel on the same data: same tolerance class (not bit-identical: different summation tree)
+    plain = np.asarray(kernels.matmul(da, db, bias=dbias, act=fact, math=_cabi.MATH_SAFE))
+    ok, msg = close(plain, want)
+    assert ok, msg
