@@ -6,8 +6,12 @@
 // Index arithmetic is 32-bit with multiply-high division (fastdiv.cuh).
 // The generic kernel rounds the kh*kw products individually (no FMA contraction) and sums them in the order
 // numpy's pairwise float32 reduction uses, so its pre-bias value is bit-identical to the reference.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fastdiv.cuh"
+#include "tc_ptx.cuh"
+#include "tma_util.cuh"
 
 namespace b200ov {
 
@@ -173,6 +177,172 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_strip_kernel(DwStripP p, con
   }
 }
 
+// ---- 3x3, TMA-staged tiles (the hot path) -------------------------------------------------------------------------------
+// Same tiling as the TMA MaxPool kernel (pool.cu): a work item is NIMG images x TR output rows x TW output columns
+// (NIMG * TW <= 32) x 32 channels; its input window, halo included, arrives by ONE 4-D bulk tensor copy into a 3-stage
+// shared-memory ring, out-of-bounds elements zero-filled by TMA = the reference's zero padding (GroupConvolution.py:62-63).
+// A consumer thread owns one output column x 4 channels and walks down the rows with the 3x3 input window in registers
+// (S new input rows per output row: 3*S 128-bit LDS instead of 9), nine packed FFMA2 pairs from the bias like the strip
+// kernel (identical arithmetic and summation order, so both give the same bits).
+struct DwTmaP {
+  int n, c, oh, ow, y_ld;
+  int pt, pl;
+  int tw, tr, nimg, bw, bh;
+  int stage_bytes;
+  float lo, hi;
+  uint32_t items;
+  FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
+};
+constexpr int DW_TMA_THREADS = 512;
+constexpr int DW_TMA_STAGES = 3;
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const DwTmaP p, const __grid_constant__ CUtensorMap map_x,
+                                                                         const float* __restrict__ wp, const float* __restrict__ bias,
+                                                                         float* __restrict__ y) {
+  using namespace ptx;
+  extern __shared__ uint8_t dw_smem_raw[];
+  const uint32_t base = (smem_u32(dw_smem_raw) + 127u) & ~127u;
+  const uint8_t* base_ptr = dw_smem_raw + (base - smem_u32(dw_smem_raw));
+  const uint32_t bars = base + DW_TMA_STAGES * p.stage_bytes;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < DW_TMA_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    fence_mbar_init();
+    prefetch_tensormap(&map_x);
+  }
+  __syncthreads();
+  const uint32_t my_items = p.items > blockIdx.x ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto decode = [&](uint32_t k, int& cc, int& ct, int& rt, int& ig) {
+    const uint32_t item = blockIdx.x + k * gridDim.x;
+    uint32_t q, q2, a, b, c3;
+    p.d_cchunks.divmod(item, q, a);
+    p.d_coltiles.divmod(q, q2, b);
+    p.d_rowtiles.divmod(q2, c3, q);
+    cc = (int)a; ct = (int)b; rt = (int)q; ig = (int)c3;
+  };
+  auto issue = [&](uint32_t k) {
+    int cc, ct, rt, ig;
+    decode(k, cc, ct, rt, ig);
+    const uint32_t s = k % DW_TMA_STAGES;
+    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.stage_bytes);
+    tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
+  };
+  if (tid == 0)
+    for (uint32_t k = 0; k < (uint32_t)(DW_TMA_STAGES - 1) && k < my_items; ++k) issue(k);
+
+  const int half = tid >> 8, t = tid & 255;
+  const int cg = t & 7, lane_col = t >> 3;
+  uint32_t img_l, ox_l;
+  p.d_tw.divmod((uint32_t)lane_col, img_l, ox_l);
+  const bool lane_ok = (int)img_l < p.nimg;
+  const int rows_half = (p.tr + 1) >> 1;
+  const int r_begin = half * rows_half, r_end = min(p.tr, r_begin + rows_half);
+  int cur_c0 = -1;
+  ulonglong2 wt[9], bv = make_ulonglong2(0ull, 0ull);
+
+  for (uint32_t k = 0; k < my_items; ++k) {
+    if (tid == 0 && k + DW_TMA_STAGES - 1 < my_items) issue(k + DW_TMA_STAGES - 1);
+    int cc, ct, rt, ig;
+    decode(k, cc, ct, rt, ig);
+    const uint32_t s = k % DW_TMA_STAGES;
+    const int c0 = cc * 32 + cg * 4;
+    const int img = ig * p.nimg + (int)img_l;
+    const int ox = ct * p.tw + (int)ox_l;
+    const bool active = lane_ok && img < p.n && ox < p.ow && c0 < p.c;
+    if (active && c0 != cur_c0) {                          // weights of this channel quad (while the tile is still in flight)
+      cur_c0 = c0;
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) wt[tp] = __ldg(reinterpret_cast<const ulonglong2*>(wp + tp * p.c + c0));
+      bv = bias != nullptr ? __ldg(reinterpret_cast<const ulonglong2*>(bias + c0)) : make_ulonglong2(0ull, 0ull);
+    }
+    mbar_wait(bars + 8 * s, (k / DW_TMA_STAGES) & 1);
+    if (active) {
+      const float* tile = reinterpret_cast<const float*>(base_ptr + s * p.stage_bytes) +
+                          ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
+      auto load_row = [&](int lr, ulonglong2 (&dst)[3]) {
+        const float* rp = tile + (size_t)lr * p.bw * 32;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) dst[kx] = *reinterpret_cast<const ulonglong2*>(rp + kx * 32);
+      };
+      ulonglong2 R[3][3];
+      constexpr int KEEP = 3 - S;                           // 2 (stride 1) or 1 (stride 2)
+#pragma unroll
+      for (int i = 0; i < KEEP; ++i) load_row(r_begin * S + i, R[i]);
+      const int oy0 = rt * p.tr;
+      float* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
+      const size_t yrow = (size_t)p.ow * p.y_ld;
+      for (int r = r_begin; r < r_end && oy0 + r < p.oh; ++r) {
+#pragma unroll
+        for (int i = KEEP; i < 3; ++i) load_row(r * S + i, R[i]);
+        f32x2 lo = bv.x, hi = bv.y;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            lo = fma2(R[ky][kx].x, wt[ky * 3 + kx].x, lo);
+            hi = fma2(R[ky][kx].y, wt[ky * 3 + kx].y, hi);
+          }
+        const float2 a = unpack2(lo), b = unpack2(hi);
+        *reinterpret_cast<float4*>(yp) = make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi),
+                                                     act_t<ACT>(b.x, p.lo, p.hi), act_t<ACT>(b.y, p.lo, p.hi));
+        yp += yrow;
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) R[i][kx] = R[i + S][kx];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q) {
+  const int K = 3, S = d->sh;
+  const int col_tiles = ceil_div(d->ow, 32);
+  q.tw = ceil_div(d->ow, col_tiles);
+  q.nimg = 32 / q.tw;
+  if (q.nimg > d->n) q.nimg = d->n;
+  if (q.nimg < 1) q.nimg = 1;
+  q.bw = (q.tw - 1) * S + K;
+  const int budget = 64 * 1024;
+  int tr = d->oh;
+  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) {
+    q.nimg = 1;
+    tr = d->oh;
+    while (tr > 1 && ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+  }
+  const int row_tiles = ceil_div(d->oh, tr);
+  q.tr = ceil_div(d->oh, row_tiles);
+  q.bh = (q.tr - 1) * S + K;
+  q.stage_bytes = q.nimg * q.bh * q.bw * 128;
+  if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
+  const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
+  const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
+  if (items <= 0 || items > 0x7fffffffLL) return false;
+  q.items = (uint32_t)items;
+  q.n = d->n; q.c = d->c; q.oh = d->oh; q.ow = d->ow; q.y_ld = d->y_ld; q.pt = d->pt; q.pl = d->pl;
+  q.lo = d->act_lo; q.hi = d->act_hi;
+  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(col_tiles); q.d_rowtiles = FastDiv(row_tiles); q.d_tw = FastDiv(q.tw);
+  return true;
+}
+
+template <int S, int ACT>
+static int launch_dw_tma(const DwTmaP& q, const CUtensorMap& map, const float* wp, const float* bias, float* y, cudaStream_t s) {
+  auto kern = dwconv3x3_tma_kernel<S, ACT>;
+  static bool configured = false;
+  if (!configured) {
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * 72 * 1024 + 8 * DW_TMA_STAGES + 256));
+    configured = true;
+  }
+  const int need = DW_TMA_STAGES * q.stage_bytes + 8 * DW_TMA_STAGES + 256;
+  const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
+  kern<<<grid, DW_TMA_THREADS, need, s>>>(q, map, wp, bias, y);
+  B200OV_LAUNCH_CHECK("dwconv3x3_tma_kernel");
+  return B200OV_OK;
+}
+
 // ---- generic window (runtime kh x kw), one output per thread --------------------------------------------
 // numpy `pairwise_sum` order for one run of KK float32 terms (KK <= 128):
 //   KK < 8  : sequential
@@ -299,7 +469,26 @@ int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_
                    aligned16(w_packed) && (bias == nullptr || aligned16(bias));
   const int V = vec ? 4 : 1;
   const int cg = d->c / V;
-  if (vec && d->math != B200OV_DW_EXACT && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) {
+  const bool hot = vec && d->math != B200OV_DW_EXACT && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2);
+  static const bool no_tma = getenv("B200OV_DW_NO_TMA") != nullptr && atoi(getenv("B200OV_DW_NO_TMA")) != 0;     // developer knob (A/B)
+  if (hot && !no_tma && d->act <= B200OV_ACT_CLAMP && (long long)d->n * d->oh * d->ow * d->c >= (1 << 16)) {
+    DwTmaP tq;
+    CUtensorMap map;
+    if (dw_tma_plan(d, tq) && tma::make_map_nhwc(&map, x, 4, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
+#define B200OV_DWT(S_, A_) return launch_dw_tma<S_, A_>(tq, map, w_packed, bias, y, s)
+      if (d->sh == 1) {
+        if (d->act == B200OV_ACT_NONE) B200OV_DWT(1, B200OV_ACT_NONE);
+        if (d->act == B200OV_ACT_RELU) B200OV_DWT(1, B200OV_ACT_RELU);
+        B200OV_DWT(1, B200OV_ACT_CLAMP);
+      } else {
+        if (d->act == B200OV_ACT_NONE) B200OV_DWT(2, B200OV_ACT_NONE);
+        if (d->act == B200OV_ACT_RELU) B200OV_DWT(2, B200OV_ACT_RELU);
+        B200OV_DWT(2, B200OV_ACT_CLAMP);
+      }
+#undef B200OV_DWT
+    }
+  }
+  if (hot) {
     DwStripP q;
     q.h = d->h; q.w = d->w; q.c = d->c; q.pt = d->pt; q.pl = d->pl; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld;
     q.y_ld = d->y_ld; q.act = d->act; q.lo = d->act_lo; q.hi = d->act_hi;

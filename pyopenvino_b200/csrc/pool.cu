@@ -13,8 +13,12 @@
 //       output instead of 9 (the LSU / L1 wavefront rate, not HBM, is what limits the naive form).
 //       32-bit index arithmetic with multiply-high division (fastdiv.cuh).
 //   pool_kernel           : every other window (and AvgPool), one thread per output, runtime loops.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fastdiv.cuh"
+#include "tc_ptx.cuh"
+#include "tma_util.cuh"
 
 namespace b200ov {
 
@@ -132,6 +136,186 @@ __global__ void __launch_bounds__(256) pool_max_strip_kernel(PoolStripP p, const
   }
 }
 
+// ---- MaxPool, TMA-staged tiles (the hot path) ----------------------------------------------------------------------------
+// A work item is a tile of the OUTPUT: NIMG images x TR rows x TW columns (NIMG * TW <= 32) x 32 channels.  One elected
+// thread fetches the input window of the tile -- ((TR-1)*S + K) x ((TW-1)*S + K) pixels x 32 channels per image, halo
+// included -- with a single 4-D bulk tensor copy (cp.async.bulk.tensor) into a 3-stage shared-memory ring; the box
+// origin may be negative / overhang the tensor and TMA fills those elements with zeros, which is precisely the
+// reference's np.pad(..., 'constant') whose zeros take part in the max (MaxPool.py:53).  Positions beyond the PADDED
+// tensor (ceil-mode overhang, clipped by min(h, ...) in MaxPool.py:69) are masked out by the consumers.
+// 512 consumer threads = 2 row halves x 32 column lanes x 8 channel quads: a thread walks down one output column with
+// rolling horizontal maxima (K - S input rows are shared by vertically adjacent windows), 128-bit LDS (a warp reads 4
+// whole 128-byte pixel chunks: conflict-free) and one 128-bit global store per output.  Loads for the next two tiles
+// are always in flight (~100-190 KB per SM), so HBM latency is covered without occupancy or registers.
+struct PoolTmaP {
+  int n, c, oh, ow, y_ld;
+  int pt, pl, hp, wpad;
+  int tw, tr, nimg, bw, bh;
+  int stage_bytes;
+  uint32_t items;
+  FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
+};
+
+constexpr int POOL_TMA_THREADS = 512;
+constexpr int POOL_TMA_STAGES = 3;
+
+template <int K, int S>
+__global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const PoolTmaP p, const __grid_constant__ CUtensorMap map_x,
+                                                                          const float* __restrict__ scale,
+                                                                          const float* __restrict__ shift, float* __restrict__ y) {
+  using namespace ptx;
+  extern __shared__ uint8_t pool_smem_raw[];
+  const uint32_t base = (smem_u32(pool_smem_raw) + 127u) & ~127u;
+  const uint8_t* base_ptr = pool_smem_raw + (base - smem_u32(pool_smem_raw));
+  const uint32_t bars = base + POOL_TMA_STAGES * p.stage_bytes;          // full[STAGES]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < POOL_TMA_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    fence_mbar_init();
+    prefetch_tensormap(&map_x);
+  }
+  __syncthreads();
+  const uint32_t my_items = p.items > blockIdx.x ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto decode = [&](uint32_t k, int& cc, int& ct, int& rt, int& ig) {
+    const uint32_t item = blockIdx.x + k * gridDim.x;
+    uint32_t q, q2, a, b, c3;
+    p.d_cchunks.divmod(item, q, a);
+    p.d_coltiles.divmod(q, q2, b);
+    p.d_rowtiles.divmod(q2, c3, q);
+    cc = (int)a; ct = (int)b; rt = (int)q; ig = (int)c3;
+  };
+  auto issue = [&](uint32_t k) {
+    int cc, ct, rt, ig;
+    decode(k, cc, ct, rt, ig);
+    const uint32_t s = k % POOL_TMA_STAGES;
+    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.stage_bytes);
+    tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
+  };
+  if (tid == 0)
+    for (uint32_t k = 0; k < (uint32_t)(POOL_TMA_STAGES - 1) && k < my_items; ++k) issue(k);
+
+  // fixed per-thread geometry
+  const int half = tid >> 8, t = tid & 255;
+  const int cg = t & 7, lane_col = t >> 3;
+  uint32_t img_l, ox_l;
+  p.d_tw.divmod((uint32_t)lane_col, img_l, ox_l);
+  const bool lane_ok = (int)img_l < p.nimg;
+  const int rows_half = (p.tr + 1) >> 1;
+  const int r_begin = half * rows_half, r_end = min(p.tr, r_begin + rows_half);
+  constexpr int KEEP = K > S ? K - S : 0;
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+
+  for (uint32_t k = 0; k < my_items; ++k) {
+    if (tid == 0 && k + POOL_TMA_STAGES - 1 < my_items) issue(k + POOL_TMA_STAGES - 1);     // its stage was drained in iteration k - 1
+    int cc, ct, rt, ig;
+    decode(k, cc, ct, rt, ig);
+    const uint32_t s = k % POOL_TMA_STAGES;
+    mbar_wait(bars + 8 * s, (k / POOL_TMA_STAGES) & 1);
+    const int c0 = cc * 32 + cg * 4;
+    const int img = ig * p.nimg + (int)img_l;
+    const int ox = ct * p.tw + (int)ox_l;
+    if (lane_ok && img < p.n && ox < p.ow && c0 < p.c && (int)ox_l < p.tw) {
+      const float* tile = reinterpret_cast<const float*>(base_ptr + s * p.stage_bytes) +
+                          ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
+      bool col_ok[K];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) col_ok[kx] = ox * S + kx < p.wpad;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (scale != nullptr) sc = __ldg(reinterpret_cast<const float4*>(scale + c0));
+      if (shift != nullptr) sf = __ldg(reinterpret_cast<const float4*>(shift + c0));
+      const int oy0 = rt * p.tr;
+      // horizontal maximum of tile row `lr` (padded row oy0*S + lr); -inf when the row lies beyond the padded tensor
+      auto hmax = [&](int lr) -> float4 {
+        if (oy0 * S + lr >= p.hp) return ninf;
+        const float* rp = tile + (size_t)lr * p.bw * 32;
+        float4 m = ninf;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float4 v = *reinterpret_cast<const float4*>(rp + kx * 32);
+          if (col_ok[kx]) m = max4(m, v);
+        }
+        return m;
+      };
+      float4 keep[KEEP > 0 ? KEEP : 1];
+#pragma unroll
+      for (int i = 0; i < KEEP; ++i) keep[i] = hmax(r_begin * S + i);
+      float* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
+      const size_t yrow = (size_t)p.ow * p.y_ld;
+      for (int r = r_begin; r < r_end && oy0 + r < p.oh; ++r) {
+        float4 o = ninf;
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) o = max4(o, keep[i]);
+        float4 fresh[K - KEEP];
+#pragma unroll
+        for (int i = 0; i < K - KEEP; ++i) {
+          fresh[i] = hmax(r * S + KEEP + i);
+          o = max4(o, fresh[i]);
+        }
+        // rows shared with the next window: the last KEEP of this window's K rows
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+          const int src = S + i;                        // index into this window's rows 0..K-1
+          keep[i] = src < KEEP ? keep[src] : fresh[src - KEEP];
+        }
+        if (scale != nullptr) { o.x = __fmul_rn(o.x, sc.x); o.y = __fmul_rn(o.y, sc.y); o.z = __fmul_rn(o.z, sc.z); o.w = __fmul_rn(o.w, sc.w); }
+        if (shift != nullptr) { o.x = __fadd_rn(o.x, sf.x); o.y = __fadd_rn(o.y, sf.y); o.z = __fadd_rn(o.z, sf.z); o.w = __fadd_rn(o.w, sf.w); }
+        *reinterpret_cast<float4*>(yp) = o;
+        yp += yrow;
+      }
+    }
+    __syncthreads();                                      // stage s is free again
+  }
+}
+
+// Tile geometry for the TMA kernel; false when the shape does not fit (the strip / generic kernels take over).
+static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q) {
+  const int K = d->kh, S = d->sh;
+  if (d->ow <= 0 || d->oh <= 0) return false;
+  const int col_tiles = ceil_div(d->ow, 32);
+  q.tw = ceil_div(d->ow, col_tiles);
+  q.nimg = 32 / q.tw;
+  if (q.nimg > d->n) q.nimg = d->n;
+  if (q.nimg < 1) q.nimg = 1;
+  q.bw = (q.tw - 1) * S + K;
+  const int budget = 64 * 1024;
+  int tr = d->oh;
+  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) {       // several images do not fit even one row
+    q.nimg = 1;
+    tr = d->oh;
+    while (tr > 1 && ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+  }
+  const int row_tiles = ceil_div(d->oh, tr);
+  q.tr = ceil_div(d->oh, row_tiles);
+  q.bh = (q.tr - 1) * S + K;
+  q.stage_bytes = q.nimg * q.bh * q.bw * 128;
+  if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
+  const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
+  const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
+  if (items <= 0 || items > 0x7fffffffLL) return false;
+  q.items = (uint32_t)items;
+  q.n = d->n; q.c = d->c; q.oh = d->oh; q.ow = d->ow; q.y_ld = d->y_ld; q.pt = d->pt; q.pl = d->pl;
+  q.hp = d->h + d->pt + d->pb; q.wpad = d->w + d->pl + d->pr;
+  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(col_tiles); q.d_rowtiles = FastDiv(row_tiles); q.d_tw = FastDiv(q.tw);
+  return true;
+}
+
+template <int K, int S>
+static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const float* scale, const float* shift, float* y, cudaStream_t s) {
+  auto kern = pool_max_tma_kernel<K, S>;
+  static bool configured = false;
+  const int smem = POOL_TMA_STAGES * 72 * 1024 + 8 * POOL_TMA_STAGES + 256;
+  if (!configured) {
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int need = POOL_TMA_STAGES * q.stage_bytes + 8 * POOL_TMA_STAGES + 256;
+  const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
+  kern<<<grid, POOL_TMA_THREADS, need, s>>>(q, map, scale, shift, y);
+  B200OV_LAUNCH_CHECK("pool_max_tma_kernel");
+  return B200OV_OK;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restrict__ x, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, float* __restrict__ y) {
@@ -223,7 +407,21 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   if (d->n == 0) return B200OV_OK;
   const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned16(x) && aligned16(y) &&
                    (scale == nullptr || aligned16(scale)) && (shift == nullptr || aligned16(shift));
-  if (vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) {
+  const bool hot = vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && d->sh == d->sw && (d->sh == 1 || d->sh == 2);
+  static const bool no_tma = getenv("B200OV_POOL_NO_TMA") != nullptr && atoi(getenv("B200OV_POOL_NO_TMA")) != 0;     // developer knob (A/B)
+  if (hot && !no_tma && (long long)d->n * d->oh * d->ow * d->c >= (1 << 16)) {
+    PoolTmaP tq;
+    CUtensorMap map;
+    if (pool_tma_plan(d, tq) &&
+        tma::make_map_nhwc(&map, x, 4, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
+      cudaStream_t s = as_stream(stream);
+      if (d->kh == 3 && d->sh == 1) return launch_pool_tma<3, 1>(tq, map, scale, shift, y, s);
+      if (d->kh == 3) return launch_pool_tma<3, 2>(tq, map, scale, shift, y, s);
+      if (d->sh == 1) return launch_pool_tma<2, 1>(tq, map, scale, shift, y, s);
+      return launch_pool_tma<2, 2>(tq, map, scale, shift, y, s);
+    }
+  }
+  if (hot) {
     PoolStripP q;
     q.h = d->h; q.w = d->w; q.pt = d->pt; q.pl = d->pl; q.hp = d->h + d->pt + d->pb;
     q.wpad = d->w + d->pl + d->pr; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld; q.y_ld = d->y_ld;

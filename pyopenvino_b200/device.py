@@ -120,34 +120,67 @@ def synchronize():
 
 
 class Arena:
-    """Bump allocator over a few large torch buffers.  `reset()` rewinds it; an identical sequence of
-    `alloc` calls then returns identical addresses, which is what lets one eager warm-up run size the
-    arena and a second, captured run be replayed as a CUDA graph."""
+    """Per-inference buffer allocator over a few large torch buffers.
+
+    `reset()` rewinds it; an identical sequence of `alloc` / `release` calls then returns identical addresses, which is
+    what lets one eager warm-up run size the arena and a second, captured run be replayed as a CUDA graph.
+    `release(t)` hands a buffer back (the executor calls it when the last consumer of a feature map has been queued:
+    liveness-planned reuse, SURVEY.md 8(b) "ownership"); later requests take the best-fitting free chunk before the
+    bump pointer moves.  Kernels run in stream order, so handing a chunk to a later producer is safe."""
 
     ALIGN = 64            # floats (256 B)
     BLOCK = 64 << 20      # floats per block (256 MB) unless a single request is larger
 
     def __init__(self):
         self.blocks = []
-        self.block_idx = 0
-        self.cursor = 0
         self.frozen = False
-        self.high_water = 0
+        self.reset()
+        self.high_water = 0          # floats in use at the peak of the last pass (live chunks, not block capacity)
 
     def reset(self):
         self.block_idx = 0
         self.cursor = 0
+        self.free = []               # [(block, offset, size)] sorted by (block, offset)
+        self.live = {}               # data_ptr -> (block, offset, size)
+        self.in_use = 0
+        self.peak = 0
+        self.allocs = 0
+        self.reused = 0
+
+    def _take(self, blk, off, n):
+        out = self.blocks[blk][off:off + n]
+        self.live[out.data_ptr()] = (blk, off, n)
+        self.in_use += n
+        self.allocs += 1
+        if self.in_use > self.peak:
+            self.peak = self.in_use
+            self.high_water = max(self.high_water, self.peak)
+        return out
 
     def alloc(self, nfloats):
         n = max(int(nfloats), 1)
         n = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        best = -1
+        for i, (blk, off, size) in enumerate(self.free):            # best fit among released chunks
+            if size >= n and (best < 0 or size < self.free[best][2]):
+                best = i
+        if best >= 0:
+            blk, off, size = self.free.pop(best)
+            if size > n:
+                self.free.append((blk, off + n, size - n))
+                self.free.sort()
+            self.reused += 1
+            return self._take(blk, off, n)
         while True:
             if self.block_idx < len(self.blocks):
-                blk = self.blocks[self.block_idx]
-                if self.cursor + n <= blk.numel():
-                    out = blk[self.cursor:self.cursor + n]
+                cap = self.blocks[self.block_idx].numel()
+                if self.cursor + n <= cap:
+                    off = self.cursor
                     self.cursor += n
-                    return out
+                    return self._take(self.block_idx, off, n)
+                if self.cursor < cap:                               # the tail of this block stays usable for small requests
+                    self.free.append((self.block_idx, self.cursor, cap - self.cursor))
+                    self.free.sort()
                 self.block_idx += 1
                 self.cursor = 0
                 continue
@@ -155,8 +188,33 @@ class Arena:
                 raise _cabi.B200ovError('arena grew during CUDA-graph capture/replay; the warm-up run did not cover this allocation')
             self.blocks.append(torch.empty(max(n, self.BLOCK), dtype=torch.float32, device='cuda'))
 
+    def owns(self, t):
+        return t.data_ptr() in self.live
+
+    def release(self, t):
+        """Give the chunk that starts at `t.data_ptr()` back; neighbouring free chunks are merged."""
+        chunk = self.live.pop(t.data_ptr(), None)
+        if chunk is None:
+            return False
+        self.in_use -= chunk[2]
+        self.free.append(chunk)
+        self.free.sort()
+        merged = []
+        for c in self.free:
+            if merged and merged[-1][0] == c[0] and merged[-1][1] + merged[-1][2] == c[1]:
+                merged[-1] = (c[0], merged[-1][1], merged[-1][2] + c[2])
+            else:
+                merged.append(c)
+        self.free = merged
+        return True
+
     def bytes(self):
+        """Device memory held by the arena (block capacity)."""
         return sum(b.numel() for b in self.blocks) * 4
+
+    def peak_bytes(self):
+        """Bytes simultaneously live at the peak of the last pass (the working set)."""
+        return self.peak * 4
 
 
 _arena = None

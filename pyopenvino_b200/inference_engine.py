@@ -96,10 +96,10 @@ class IECore:
 
     # OpenVINO Inference Engine API
     def load_network(self, network, device_name: str = 'B200', num_requests: int = 1, batch_size: int = None,
-                     fuse: bool = True, use_graph: bool = True):
+                     fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True):
         if batch_size is not None and batch_size != network.batch_size:
             network.set_batch_size(batch_size)
-        exenet = Executable_Network(network, fuse=fuse, use_graph=use_graph)
+        exenet = Executable_Network(network, fuse=fuse, use_graph=use_graph, reuse_buffers=reuse_buffers)
         self.check_nodes(exenet.ienet.G)
         exenet.schedule_tasks()
         return exenet
@@ -223,13 +223,72 @@ class IENetwork:
 
 # -------------------------------------------------------------------------------------------------
 
+class _Liveness:
+    """Liveness-planned reuse of per-inference buffers (SURVEY.md 8(f) NEXT-3; ownership rule `inference_engine.py:290-292`:
+    the reference keeps every feature map until the next inference only because nothing frees them -- no caller reads them
+    after `infer`).  Active in planned CUDA-graph mode only.
+
+    Every arena chunk counts the consumer steps still to be queued over all graph nodes whose output lives in it (views --
+    Reshape, NHWC Transpose, channel slices of an in-place Concat -- share their producer's chunk).  When the count reaches
+    zero the chunk goes back to the arena and the next producer may take it.  The sequence of allocations and releases is a
+    pure function of the plan, so the warm-up pass, the captured pass and every later capture see identical addresses."""
+
+    def __init__(self, exe, arena):
+        self.exe, self.arena = exe, arena
+        self.pending = {}          # chunk base pointer -> consumer steps not yet queued
+        self.node_chunk = {}       # graph node id -> chunk base pointer of its stored output
+        self.pinned = set()        # chunks that must survive the pass (Result tensors)
+
+    def _consumers(self, node_id):
+        G, plan = self.exe.ienet.G, self.exe._plan
+        return sum(1 for s in G.successors(node_id) if not plan[s]['skip'] and not plan[s].get('const_done'))
+
+    def stored(self, node_id, data):
+        """`data` was stored as the output of graph node `node_id`."""
+        t = getattr(data, 't', None)
+        if t is None or not self.arena.owns(t):
+            return
+        key = t.data_ptr()
+        self.node_chunk[node_id] = key
+        self.pending[key] = self.pending.get(key, 0) + self._consumers(node_id)
+
+    def pin(self, data):
+        t = getattr(data, 't', None)
+        if t is not None and self.arena.owns(t):
+            self.pinned.add(t.data_ptr())
+
+    def consumed(self, task):
+        """Step `task` has been queued: its inputs have one consumer less."""
+        G = self.exe.ienet.G
+        for pred in G.pred[task]:
+            key = self.node_chunk.get(pred)
+            if key is None:
+                continue
+            self.pending[key] -= 1
+            if self.pending[key] <= 0 and key not in self.pinned:
+                self._release(key)
+
+    def sweep(self):
+        """Chunks whose producers have no consumer at all (dead outputs) are released at once."""
+        for key, cnt in list(self.pending.items()):
+            if cnt <= 0 and key not in self.pinned:
+                self._release(key)
+
+    def _release(self, key):
+        chunk = self.arena.live.get(key)
+        if chunk is not None:
+            self.arena.release(self.arena.blocks[chunk[0]][chunk[1]:chunk[1] + chunk[2]])
+        self.pending.pop(key, None)
+
+
 _EPILOGUE_HEADS = ('Convolution', 'GroupConvolution', 'MatMul')
 _OUT_CAPABLE = ('Convolution', 'GroupConvolution', 'MaxPool', 'AvgPool', 'LRN', 'ReLU', 'Clamp', 'Sigmoid')
 
 
 class Executable_Network:
-    def __init__(self, ienetwork: IENetwork, fuse: bool = True, use_graph: bool = True):
+    def __init__(self, ienetwork: IENetwork, fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True):
         self.ienet = ienetwork
+        self.reuse_buffers = reuse_buffers and os.environ.get('B200OV_NO_REUSE') != '1'
         self.expected_result = None     # {node_name: [precision, dims, ndarray]} feature-map ground truth (debug)
         self.kernel_type = 'naive'      # accepted for compatibility: every value runs the CUDA kernels
         self.pickle_node_args = []      # node ids whose (node, inputs) are pickled for node unit tests (eager mode)
@@ -467,6 +526,10 @@ class Executable_Network:
         plan = self._plan if self._plan is not None else self.build_plan()
         concat_bufs = {}
         group_done = set()
+        from . import device as _dev
+        arena = _dev.current_arena()
+        live = _Liveness(self, arena) if (capture and arena is not None and self.reuse_buffers) else None
+        self._live = live
         for task in self.task_list:
             node = G.nodes[task]
             step = plan[task]
@@ -478,6 +541,9 @@ class Executable_Network:
                     kernels.default_math == kernels._cabi.MATH_AUTO and self.expected_result is None and not self.pickle_node_args:
                 if self._run_group(step['group'], concat_bufs):
                     group_done.update(step['group'])
+                    if live is not None:
+                        for m in step['group']:
+                            live.consumed(m)
                     continue
             node_type = node['type']
             if node_type not in p.plugins:
@@ -513,6 +579,9 @@ class Executable_Network:
             if capture and node_type == 'Result':
                 x = inputs[0]
                 self._static_out[node['name']] = kernels.as_plain(x) if is_device(x) else x
+                if live is not None:
+                    live.pin(x)
+                    live.pin(self._static_out[node['name']])
                 continue
             if verbose:
                 print('{}, {}, {}, '.format(task, node_type, node['name']), end=' ', flush=True)
@@ -549,6 +618,12 @@ class Executable_Network:
                 for port_id, data in res.items():
                     tport = port_id if step['store_as'] == task else common_def.first_output_port(target)
                     target['output'][tport]['data'] = data
+                    if live is not None:
+                        live.stored(step['store_as'], data)
+            if live is not None:
+                live.consumed(task)
+        if live is not None:
+            live.sweep()
 
     def _run_group(self, members, concat_bufs):
         """Sibling 1x1 convolutions as one multi-output contraction.  False -> run the members one by one."""
@@ -589,6 +664,8 @@ class Executable_Network:
         for m, y in zip(members, outs):
             target = G.nodes[plan[m]['store_as']]
             target['output'][common_def.first_output_port(target)]['data'] = y
+            if getattr(self, '_live', None) is not None:
+                self._live.stored(plan[m]['store_as'], y)
         return True
 
     def run_tasks(self, verbose: bool = False):

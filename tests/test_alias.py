@@ -13,7 +13,14 @@ from conftest import GOLDEN, REPO
 
 
 def _run(code_or_path, *args, is_path=False):
-    cmd = [sys.executable] + ([code_or_path] if is_path else ['-c', code_or_path]) + list(args)
+    if is_path:
+        # the reference's scripts sit in the repo root, so python puts the root (their directory) on sys.path; ours sit in
+        # tests/scripts/: run them unedited with sys.path[0] = repo root, exactly what a root-level script gets
+        boot = ('import runpy, sys; sys.path.insert(0, {root!r}); sys.argv = sys.argv[1:]; '
+                'runpy.run_path(sys.argv[0], run_name="__main__")').format(root=REPO)
+        cmd = [sys.executable, '-c', boot, code_or_path] + list(args)
+    else:
+        cmd = [sys.executable, '-c', code_or_path] + list(args)
     env = dict(os.environ)
     env.pop('PYTHONPATH', None)
     return subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=600)

@@ -322,3 +322,101 @@ def test_matmul_split_k_vs_oracle(m, k, n, act):
     plain = np.asarray(kernels.matmul(da, db, bias=dbias, act=fact, math=_cabi.MATH_SAFE))
     ok, msg = close(plain, want)
     assert ok, msg
+
+
+# ---- liveness-planned arena ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('model,batch', [('googlenet-v1', 16), ('ssd_mobilenet_v1_coco', 4), ('mnist_bn', 64)])
+def test_buffer_reuse_is_bit_identical_and_smaller(model_dir, model, batch):
+    """Released feature-map buffers are handed to later producers (planned CUDA-graph mode).  Results are bit-identical
+    to the run that keeps every buffer, replay after replay, and the live working set shrinks."""
+    from tools.synth_bin import synth_input
+    x = synth_input(model, batch=batch, seed=12)
+    x2 = synth_input(model, batch=batch, seed=13)
+    net_a, exe_a = _load(model_dir, model, batch=batch, reuse_buffers=False)
+    net_b, exe_b = _load(model_dir, model, batch=batch, reuse_buffers=True)
+    name, out = net_a.inputs[0]['name'], net_a.outputs[0]['name']
+    for xx in (x, x2, x):
+        a = exe_a.infer({name: xx})[out]
+        b = exe_b.infer({name: xx})[out]
+        assert np.array_equal(a, b)
+    keep_all, reuse = exe_a._arena.peak_bytes(), exe_b._arena.peak_bytes()
+    assert exe_b._arena.reused > 0
+    assert reuse < 0.6 * keep_all, (keep_all, reuse)
+    # a second input signature (uint8) captures another graph over the same arena
+    x8 = np.random.default_rng(1).integers(0, 256, x.shape, dtype=np.uint8)
+    assert np.array_equal(exe_a.infer({name: x8})[out], exe_b.infer({name: x8})[out])
+    assert np.array_equal(exe_b.infer({name: x})[out], exe_a.infer({name: x})[out])
+
+
+# ---- TMA-staged MaxPool / depthwise tiles ------------------------------------------------------------------------------
+
+def _maybe_slice(kernels, x_host, rng):
+    """Upload an NCHW array as NHWC, half of the time as a channel slice of a wider (Concat-style) buffer."""
+    n, c, h, w = x_host.shape
+    if rng.integers(0, 2) == 0:
+        return kernels.to_nhwc(kernels.upload(x_host))
+    extra = 4 * int(rng.integers(1, 5))
+    lead = 4 * int(rng.integers(0, 3))
+    wide = np.full((n, lead + c + extra, h, w), np.float32(1e9))       # poison around the slice
+    wide[:, lead:lead + c] = x_host
+    buf = kernels.to_nhwc(kernels.upload(wide.astype(np.float32)))
+    return kernels.channel_slice(buf, lead, c)
+
+
+def test_tma_maxpool_tiles_vs_oracle():
+    """pool_max_tma_kernel over the tile geometries the planner produces (several images per tile, row / column tiles,
+    partial channel chunks, ceil-mode overhang beyond the padded tensor, zero padding that takes part in the max,
+    channel-slice inputs and outputs): bit-exact against the oracle."""
+    from oracle import ref_ops
+    from pyopenvino_b200 import _cabi, common_def, kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(21)
+    cases = 0
+    for hw in (7, 10, 14, 19, 28, 33, 56, 75, 112):
+        for (k, s, p, rounding) in ((3, 1, 1, 'ceil'), (3, 2, 0, 'ceil'), (3, 2, 1, 'floor'), (2, 2, 0, 'floor'), (2, 1, 0, 'ceil'), (3, 1, 0, 'floor')):
+            c = int(rng.choice([16, 36, 64, 96, 132]))
+            n = int(rng.integers(1, 10))
+            while n * c * hw * hw < (1 << 17):
+                n += 1
+            x = (rng.standard_normal((n, c, hw, hw)) * 2 - (1.5 if rng.integers(0, 2) else 0.0)).astype(np.float32)
+            data = {'strides': '{0},{0}'.format(s), 'kernel': '{0},{0}'.format(k), 'pads_begin': '{0},{0}'.format(p),
+                    'pads_end': '{0},{0}'.format(p), 'rounding_type': rounding, 'auto_pad': 'explicit'}
+            want = ref_ops.maxpool(data, x)
+            oh, ow = want.shape[2:]
+            xd = _maybe_slice(kernels, x, rng)
+            out = None
+            if rng.integers(0, 2):
+                out = kernels.channel_slice(kernels.new_nhwc(n, c + 8, oh, ow), 4, c)
+            y = kernels.pool2d(xd, _cabi.POOL_MAX, (k, k), (s, s), (p, p), (p, p), (oh, ow), out=out)
+            assert np.array_equal(np.asarray(y), want), (hw, k, s, p, rounding, n, c)
+            cases += 1
+    assert cases == 54
+
+
+def test_tma_depthwise_tiles_vs_oracle():
+    """dwconv3x3_tma_kernel: FP32 tolerance class against the oracle over the planner's tile geometries, both strides,
+    asymmetric pads, bias + Clamp epilogue, channel-slice inputs."""
+    from oracle import ref_ops
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(22)
+    for hw in (10, 19, 38, 75, 150, 23):
+        for s in (1, 2):
+            c = int(rng.choice([32, 48, 128, 516]))
+            n = int(rng.integers(1, 6))
+            while n * c * hw * hw < (1 << 18):
+                n += 1
+            pb = (int(rng.integers(0, 2)), int(rng.integers(0, 2)))
+            pe = (int(rng.integers(0, 2)), int(rng.integers(0, 2)))
+            x = rng.standard_normal((n, c, hw, hw)).astype(np.float32)
+            w = (rng.standard_normal((c, 1, 1, 3, 3)) * 0.5).astype(np.float32)
+            b = (0.1 * rng.standard_normal((1, c, 1, 1))).astype(np.float32)
+            want = np.clip(ref_ops.groupconv_numpy(x, w, (s, s), pb, pe, 'explicit') + b, 0.0, 6.0)
+            oh, ow = want.shape[2:]
+            xd = _maybe_slice(kernels, x, rng)
+            y = kernels.dwconv2d(xd, kernels.upload(w), (s, s), pb, (oh, ow), bias=kernels.upload(b), act=('clamp', 0.0, 6.0))
+            ok, msg = close(np.asarray(y), want)
+            assert ok, ((hw, s, c, n, pb, pe), msg)
