@@ -271,7 +271,7 @@ def time_e2e(exe, in_name, out_name, x, steps, warmup, world, dtype=np.float32):
     return distributed.max_over_ranks(time.perf_counter() - t0), res[out_name]
 
 
-def measure(model, batch, desc, args, peaks, rank, world, local, primary):
+def measure(model, batch, desc, args, peaks, rank, world, local, primary, storage='f32', light=False):
     """One workload at `world` GPUs: device-timed value, e2e (FP32 and uint8 host input), per-layer roofline.
     Returns the fields of a bench line (rank 0) or None."""
     import torch
@@ -285,7 +285,7 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary):
     xml = ensure_model(model, CACHE)
     ie = IECore()
     net = ie.read_network(xml, xml[:-4] + '.bin')
-    exe = ie.load_network(net, 'B200', batch_size=batch)
+    exe = ie.load_network(net, 'B200', batch_size=batch, storage=storage)
     if args.math:
         exe.kernel_type = args.math
     in_name, out_name = net.inputs[0]['name'], net.outputs[0]['name']
@@ -330,7 +330,7 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary):
         ms_step = ms_total / steps
         # the same replay loop held for >= args.sustain seconds: does the number survive the power limit?
         sustained = None
-        if args.sustain > 0 and (primary or args.sustain_all):
+        if args.sustain > 0 and (primary or args.sustain_all) and not light:
             n_sus = max(steps, int(args.sustain * 1e3 / max(ms_step, 1e-3)) + 1)
             sus_sampler = ClockSampler(local)
             ms_sus = timed(n_sus, sus_sampler)
@@ -342,16 +342,18 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary):
         x8 = np.clip(np.rint(x if model in ('mnist', 'ssd_mobilenet_v1_coco') else x * 255.0), 0, 255).astype(np.uint8)
         e2e8_s, _ = time_e2e(exe, in_name, out_name, x8, steps, warmup, world, np.uint8)
         exe._select_graph({in_name: x})
-        # one synchronous infer() per step (no overlap), reported beside it
-        x_pinned = exe.input_buffer(in_name)
-        x_pinned[...] = x
-        exe.infer({in_name: x_pinned})
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
+        e2e_sync_s = None
+        if not light:
+            # one synchronous infer() per step (no overlap), reported beside it
+            x_pinned = exe.input_buffer(in_name)
+            x_pinned[...] = x
             exe.infer({in_name: x_pinned})
-        torch.cuda.synchronize()
-        e2e_sync_s = distributed.max_over_ranks(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                exe.infer({in_name: x_pinned})
+            torch.cuda.synchronize()
+            e2e_sync_s = distributed.max_over_ranks(time.perf_counter() - t0)
     distributed.barrier()
 
     images = batch * world * steps
@@ -359,6 +361,20 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary):
     if rank != 0:
         del exe
         return None
+    if light:
+        res.update({'storage': storage, 'arena_mb': exe._arena.bytes() / 1e6, 'working_set_mb': exe._arena.peak_bytes() / 1e6,
+                    'launches_per_step': launches_per_step, 'clocks': sampler.summary(),
+                    'e2e': {'value': images / e2e_s, 'unit': 'images/s', 'input_dtype': 'float32', 'ms_per_step': e2e_s / steps * 1e3},
+                    'e2e_u8': {'value': images / e2e8_s, 'unit': 'images/s', 'input_dtype': 'uint8', 'ms_per_step': e2e8_s / steps * 1e3}})
+        fam = {}
+        work = __import__('tools.roofline', fromlist=['layer_work']).layer_work(exe)
+        for s_ in exe.profile_steps({in_name: x}, iters=3):
+            w = work.get(s_['id'])
+            if w is not None:
+                fam[w['kind']] = fam.get(w['kind'], 0.0) + s_['ms']
+        res['family_ms'] = fam
+        del exe
+        return res
     work, layers, fam, kern, total_ms = layer_table(exe, in_name, x, peaks)
     top_kind = max(kern, key=lambda k: kern[k]['ms'])
     res['roofline'] = kernel_roofline(top_kind, kern[top_kind], total_ms, peaks, model)
@@ -378,15 +394,17 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary):
                      'input_shape': list(x.shape), 'parallelism': 'dp{} (batch-sharded replicas, no data-path collective)'.format(world),
                      'l2': 'no flush: per-step working set {:.0f} MB > 126 MB L2'.format(working_set_mb)
                      if working_set_mb > 126 else 'working set {:.0f} MB fits L2 (not flushed)'.format(working_set_mb),
-                     'fused_cuda_graph': True, 'math': args.math or 'auto',
-                     'arena_mb': exe._arena.bytes() / 1e6 if exe._arena is not None else None}
+                     'fused_cuda_graph': True, 'math': args.math or 'auto', 'storage': storage,
+                     'arena_mb': exe._arena.bytes() / 1e6 if exe._arena is not None else None,
+                     'working_set_mb': exe._arena.peak_bytes() / 1e6 if exe._arena is not None else None}
     res['clocks'] = sampler.summary()
     if sustained is not None:
         res['sustained'] = sustained
     api = 'Executable_Network.start_async(slot=) / wait, 2 requests in flight (H2D of step i+1 overlaps step i)'
     res['e2e'] = {'value': images / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(x.nbytes) * world,
                   'd2h_bytes_per_step': int(out.nbytes) * world, 'ms_per_step': e2e_s / steps * 1e3, 'input_dtype': 'float32',
-                  'api': api, 'sync_infer_value': images / e2e_sync_s, 'sync_infer_ms_per_step': e2e_sync_s / steps * 1e3}
+                  'api': api, 'sync_infer_value': images / e2e_sync_s if e2e_sync_s else None,
+                  'sync_infer_ms_per_step': e2e_sync_s / steps * 1e3 if e2e_sync_s else None}
     res['e2e_u8'] = {'value': images / e2e8_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(x8.nbytes) * world,
                      'd2h_bytes_per_step': int(out.nbytes) * world, 'ms_per_step': e2e8_s / steps * 1e3, 'input_dtype': 'uint8',
                      'api': api, 'note': 'same images as uint8 frames (Parameter.py:13 accepts any array-like); widened on the device'}
@@ -410,6 +428,9 @@ def main():
     ap.add_argument('--sustain', type=float, default=3.0, help='seconds of back-to-back replays for the `sustained` field (0 = off)')
     ap.add_argument('--sustain-all', action='store_true', help='also for the secondary workloads')
     ap.add_argument('--no-secondary', action='store_true', help='measure only --workload')
+    ap.add_argument('--no-f16', action='store_true', help='skip the f16_storage measurement')
+    ap.add_argument('--storage', default='f32', choices=['f32', 'f16'],
+                    help="feature-map storage of the headline line (the default line always adds an `f16_storage` object beside the FP32 value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     model, default_batch, desc = WORKLOADS[args.workload]
@@ -430,9 +451,19 @@ def main():
 
     line = {'metric': METRIC, 'value': None, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic'}
-    res = measure(model, batch, desc, args, peaks, rank, world, local, primary=True)
+    res = measure(model, batch, desc, args, peaks, rank, world, local, primary=True, storage=args.storage)
     if rank == 0:
         line.update(res)
+        if args.storage != 'f32':
+            line['dtype'] = 'f32 arithmetic, f16 feature-map storage (opt-in mode; NOT the headline configuration)'
+    # opt-in FP16 feature-map storage, same workload, same run: a separately named field -- `value` above stays FP32
+    if args.storage == 'f32' and not args.no_f16:
+        r16 = measure(model, batch, desc, args, peaks, rank, world, local, primary=False, storage='f16', light=True)
+        if rank == 0:
+            r16['note'] = ("load_network(..., storage='f16'): NHWC feature maps kept in HBM as FP16, FP32 arithmetic; own tolerance "
+                           "statement in tests/test_gpu_f16_storage.py; the headline `value` / `e2e` are FP32 storage")
+            r16['speedup_vs_f32_storage'] = r16['value'] / line['value']
+            line['f16_storage'] = r16
     # the other BASELINE.json configurations, same run, same N (the driver only ever launches the default command)
     secondary = {}
     if not args.no_secondary and args.batch is None:

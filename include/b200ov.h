@@ -58,6 +58,15 @@ enum {
   B200OV_MATH_SAFE = 5      /* AUTO without F16X2 (full FP32 exponent range): 3xTF32, else FFMA  */
 };
 
+/* Element types.  Host inputs may arrive as any of them (Parameter.py:13 casts whatever array-like it is given with
+ * `np.array(param).reshape(shape).astype(precision)`; draw-and-infer.py:56-60 feeds uint8): the bytes cross PCIe in their
+ * native width and are widened on the device (exact, so bit-identical to the host cast).  F32 / F16 are also the two
+ * STORAGE types of NHWC feature maps in HBM: F32 is the reference's precision (models/*.xml ports are FP32) and the
+ * default; F16 is the opt-in storage mode (`load_network(..., storage='f16')`): every kernel still computes in FP32 and
+ * rounds to nearest even on store, halving the bytes of the bandwidth-bound layers.  The reference's plugins are
+ * dtype-generic (common_def.py:18-19) and its original IRs were FP16 (GroupConvolution.py:136-143). */
+enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3 };
+
 /* ---- library / device -------------------------------------------------------------------- */
 int b200ov_version(void);
 const char* b200ov_last_error(void);
@@ -97,6 +106,8 @@ typedef struct {
   int32_t act;                 /* B200OV_ACT_*                                                   */
   float act_lo, act_hi;        /* Clamp bounds                                                   */
   int32_t math;                /* B200OV_MATH_*                                                  */
+  int32_t x_dtype, y_dtype;    /* storage type of x / y: B200OV_DT_F32 (0, default) or B200OV_DT_F16; F16 needs the
+                                  B200OV_MATH_F16X2 path (an FP16 input IS its own hi part: 2 MMAs per product)  */
 } b200ov_conv_desc;
 
 /* OIHW -> packed [kh*kw*cin (pad 16)][ldw] (row index ordered ky, kx, ci).  `ldw` and the row
@@ -106,8 +117,8 @@ int b200ov_pack_conv_weights(const float* w_oihw, float* w_packed, int cout, int
 
 /* y = act(conv(x, w) + bias).  Replaces Convolution.compute (Convolution.py:149-176) and, through
  * the epilogue, the Add (Add.py:9-14) and ReLU / Clamp nodes that follow it.  `bias` may be NULL. */
-int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias,
-                  float* y, void* stream);
+int b200ov_conv2d(const b200ov_conv_desc* d, const void* x, const float* w_packed, const float* bias,
+                  void* y, void* stream);
 
 /* Sibling convolutions that read the same feature map with the same geometry (the 1x1 / 3x3_reduce / 5x5_reduce
  * branches of an inception module) as ONE contraction: `w_packed` / `bias` are the packed form of the weights
@@ -120,7 +131,7 @@ typedef struct {
   void* y;
   int32_t col0, cout, y_ld;
 } b200ov_conv_seg;
-int b200ov_conv2d_multi(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias,
+int b200ov_conv2d_multi(const b200ov_conv_desc* d, const void* x, const float* w_packed, const float* bias,
                         int nseg, const b200ov_conv_seg* segs, void* stream);
 
 /* Y[m][n] = act(sum_k A[m][k] * Bkn[k][n] + bias[n]); Bkn is the packed form of a 1x1 conv weight
@@ -158,6 +169,7 @@ typedef struct {
   int32_t act;
   float act_lo, act_hi;
   int32_t math;                /* B200OV_DW_*                                                    */
+  int32_t dtype;               /* storage type of x and y: B200OV_DT_F32 (0, default) or B200OV_DT_F16 (3x3 only) */
 } b200ov_dwconv_desc;
 
 enum {
@@ -171,8 +183,8 @@ int b200ov_pack_dw_weights(const float* w_g11hw, float* w_packed, int c, int kh,
  * math = B200OV_DW_EXACT: products are summed in numpy's pairwise order without FMA contraction, so the
  * pre-bias value is bit-identical to `np.sum(patch*flt)` (GroupConvolution.py:78); B200OV_DW_AUTO may use
  * an FMA chain (3x3 windows), which meets the FP32 tolerance class but is not bit-identical. */
-int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_packed, const float* bias,
-                    float* y, void* stream);
+int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const void* x, const float* w_packed, const float* bias,
+                    void* y, void* stream);
 
 /* ---- pooling --------------------------------------------------------------------------------- */
 enum { B200OV_POOL_MAX = 0, B200OV_POOL_AVG_REF = 1 };
@@ -184,12 +196,13 @@ typedef struct {
   int32_t x_ld, y_ld;
   int32_t mode;                /* MAX: zero padding takes part, overhang clipped (MaxPool.py:53,69)
                                   AVG_REF: no padding, window clipped at h-1 / w-1 (AvgPool.py:56) */
+  int32_t dtype;               /* storage type of x and y: B200OV_DT_F32 (0, default) or B200OV_DT_F16        */
 } b200ov_pool_desc;
 /* Replaces MaxPool.compute (MaxPool.py:111-135) / AvgPool.compute (AvgPool.py:94-118).  Optional
  * per-channel epilogue y = y*scale[c] + shift[c] (the folded BatchNorm Multiply+Add that follows
  * the pools of mnist_bn); either pointer may be NULL. */
-int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const float* scale, const float* shift,
-                  float* y, void* stream);
+int b200ov_pool2d(const b200ov_pool_desc* d, const void* x, const float* scale, const float* shift,
+                  void* y, void* stream);
 
 /* ---- elementwise tail -------------------------------------------------------------------------- */
 /* y[i] = act((x[i] * s) + b) over rows x C elements with channel = i % C (NHWC pixels or 2-D rows).
@@ -210,6 +223,10 @@ int b200ov_softmax(const float* x, float* y, int rows, int cols, void* stream);
 int b200ov_lrn(const float* x, float* y, int64_t pixels, int c, int x_ld, int y_ld, int size,
                float alpha, float beta, float bias, void* stream);
 
+/* b200ov_lrn on a feature map stored as `dtype` (B200OV_DT_F32 / B200OV_DT_F16), input and output alike. */
+int b200ov_lrn_st(const void* x, void* y, int dtype, int64_t pixels, int c, int x_ld, int y_ld, int size,
+                  float alpha, float beta, float bias, void* stream);
+
 /* ---- layout glue ----------------------------------------------------------------------------- */
 /* [batch][rows][cols] -> [batch][cols][rows] with an output pitch (NCHW<->NHWC, Transpose.py:9-13,
  * MatMul transpose flags).  Optional y = x*scale[c]+shift[c] on the fly when the source is NCHW
@@ -219,16 +236,18 @@ int b200ov_transpose(const float* x, float* y, int batch, int rows, int cols, in
 int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, int y_ld,
                                int has_scale, const float* scale_vec, float scale_s,
                                int has_shift, const float* shift_vec, float shift_s, void* stream);
-/* Element types a host input may arrive in.  Parameter.compute casts whatever array-like it is given with
- * `np.array(param).reshape(shape).astype(precision)` (Parameter.py:13; draw-and-infer.py:56-60 feeds uint8): here the
- * bytes cross PCIe in their native width and are widened on the device (exact, so bit-identical to the host cast). */
-enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3 };
 /* b200ov_nchw_to_nhwc_affine for an input of element type `dtype` (NCHW, dense). */
 int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int hw, int y_ld,
                          int has_scale, const float* scale_vec, float scale_s,
                          int has_shift, const float* shift_vec, float shift_s, void* stream);
 /* y[i] = (float)x[i]: a non-image (not 4-D) input of element type `dtype` (Parameter.py:13). */
 int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream);
+/* b200ov_transpose / b200ov_copy2d between storage types (F32 / F16): the FP16 storage mode's NHWC feature maps leave
+ * the device-resident path through these (NHWC f16 -> plain NCHW f32 in front of Reshape / MatMul / Result). */
+int b200ov_transpose_st(const void* x, int x_dtype, void* y, int y_dtype, int batch, int rows, int cols,
+                        int x_ld, int y_ld, void* stream);
+int b200ov_copy2d_st(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t rows, int cols,
+                     int src_ld, int dst_ld, void* stream);
 /* rows x cols strided copy (Concat.py:9-13 when producers could not write in place). */
 int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream);
 

@@ -23,13 +23,13 @@ class B200ovError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'cin', 'cout', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
                                          'x_ld', 'y_ld', 'ldw', 'act')] + \
-               [('act_lo', C.c_float), ('act_hi', C.c_float), ('math', C.c_int32)]
+               [('act_lo', C.c_float), ('act_hi', C.c_float), ('math', C.c_int32), ('x_dtype', C.c_int32), ('y_dtype', C.c_int32)]
 
 
 class DwConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
                                          'x_ld', 'y_ld', 'act')] + [('act_lo', C.c_float), ('act_hi', C.c_float),
-                                                                    ('math', C.c_int32)]
+                                                                    ('math', C.c_int32), ('dtype', C.c_int32)]
 
 
 DW_AUTO, DW_EXACT = 0, 1
@@ -41,7 +41,7 @@ class ConvSeg(C.Structure):
 
 class PoolDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'pb', 'pr', 'oh', 'ow',
-                                         'x_ld', 'y_ld', 'mode')]
+                                         'x_ld', 'y_ld', 'mode', 'dtype')]
 
 
 class DetectionDesc(C.Structure):
@@ -88,7 +88,10 @@ SIGNATURES = {
     'b200ov_binary': [_I, _P, _P, _P, _L, _P],
     'b200ov_softmax': [_P, _P, _I, _I, _P],
     'b200ov_lrn': [_P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200ov_lrn_st': [_P, _P, _I, _L, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200ov_transpose': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'b200ov_transpose_st': [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    'b200ov_copy2d_st': [_P, _I, _P, _I, _L, _I, _I, _I, _P],
     'b200ov_nchw_to_nhwc_affine': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _F, _P],
     'b200ov_input_to_nhwc': [_P, _I, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _F, _P],
     'b200ov_widen': [_P, _I, _P, _L, _P],
@@ -101,7 +104,7 @@ _lib = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it)
 
 _LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_matmul_ws', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
-              'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_transpose',
+              'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_lrn_st', 'b200ov_transpose', 'b200ov_transpose_st', 'b200ov_copy2d_st',
               'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_detection_output'}
 
 

@@ -7,12 +7,12 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
 int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
                    cudaStream_t s, bool probe_only);
 // persistent tcgen05 FP16-split path (conv_f16x2.cu)
-bool f16x2_eligible(const b200ov_conv_desc* d, const float* x);
-int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s);
-int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
+bool f16x2_eligible(const b200ov_conv_desc* d, const void* x);
+int conv2d_f16x2(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, void* y, cudaStream_t s);
+int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, int nseg,
                        const b200ov_conv_seg* segs, cudaStream_t s, int ksplit, int ws_rows);
 int f16x2_splitk_plan(int m, int cout, int cin, int kh, int kw, int* ws_rows, int* ws_ld);
-int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, float* ws,
+int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, float* y, float* ws,
                         size_t ws_bytes, cudaStream_t s);
 unsigned int* f16x2_status_word();
 bool has_tf32_section(int cin);
@@ -21,7 +21,7 @@ void tf32_weight_dims(int cout, int cin, int kh, int kw, int* coutp, long long* 
 
 using namespace b200ov;
 
-static int validate(const b200ov_conv_desc* d, const float* x, const float* wp, float* y) {
+static int validate(const b200ov_conv_desc* d, const void* x, const float* wp, void* y) {
   B200OV_REQUIRE(d && x && wp && y, "conv2d: null argument");
   B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv2d: bad tensor dims");
   B200OV_REQUIRE(d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 && d->pt >= 0 && d->pl >= 0, "conv2d: bad filter geometry");
@@ -52,11 +52,21 @@ static const float* f16_section(const b200ov_conv_desc* d, const float* w_packed
 
 extern "C" {
 
-int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias, float* y,
+int b200ov_conv2d(const b200ov_conv_desc* d, const void* x_raw, const float* w_packed, const float* bias, void* y_raw,
                   void* stream) {
-  int rc = validate(d, x, w_packed, y);
+  int rc = validate(d, x_raw, w_packed, y_raw);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
+  if (d->x_dtype != B200OV_DT_F32 || d->y_dtype != B200OV_DT_F32) {
+    // FP16 feature maps: only the f16x2 contraction reads / writes them
+    B200OV_REQUIRE((d->x_dtype == B200OV_DT_F32 || d->x_dtype == B200OV_DT_F16) && (d->y_dtype == B200OV_DT_F32 || d->y_dtype == B200OV_DT_F16),
+                   "conv2d: bad storage type");
+    if ((d->math != B200OV_MATH_AUTO && d->math != B200OV_MATH_F16X2) || !f16x2_eligible(d, x_raw))
+      return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: FP16 feature maps need the f16x2 path (cin %% 8 == 0, 16-byte aligned pixels)");
+    return conv2d_f16x2(d, x_raw, f16_section(d, w_packed), bias, y_raw, s);
+  }
+  const float* x = static_cast<const float*>(x_raw);
+  float* y = static_cast<float*>(y_raw);
   switch (d->math) {
     case B200OV_MATH_FP32:
       return conv2d_ffma(d, x, w_packed, bias, y, s);
@@ -81,7 +91,7 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const float* x, const float* w_pack
   }
 }
 
-int b200ov_conv2d_multi(const b200ov_conv_desc* d, const float* x, const float* w_packed, const float* bias, int nseg,
+int b200ov_conv2d_multi(const b200ov_conv_desc* d, const void* x, const float* w_packed, const float* bias, int nseg,
                         const b200ov_conv_seg* segs, void* stream) {
   B200OV_REQUIRE(d && x && w_packed && segs, "conv2d_multi: null argument");
   B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 &&

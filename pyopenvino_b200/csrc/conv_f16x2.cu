@@ -238,9 +238,10 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
   return r;
 }
 
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
+// A16: the input feature map is stored as FP16 (a == a_hi: no split, 4 MMAs per slot); O16: the output is stored as FP16.
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __restrict__ bias,
+conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* __restrict__ bias,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y0,
                   const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2) {
@@ -388,8 +389,13 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           const uint32_t d_main = buf * BLOCK_N;
           const uint64_t b_hi = desc_hi0 + (uint64_t)(bs * STAGE_DESC);
           const uint64_t b_lo = desc_lo0 + (uint64_t)(bs * STAGE_DESC);
-          umma_f16x2_slot(d_main, tmem_cross, a0, b_hi, b_lo, idesc, in_chunk > 0 ? 1u : 0u, slot > 0 ? 1u : 0u, bar_a_empty(as));
-          if (two) umma_f16x2_slot(d_main, tmem_cross, a1, b_hi + 4, b_lo + 4, idesc, 1u, 1u, bar_a_empty(as1));   // +64 B along K
+          if constexpr (A16) {
+            umma_f16a_slot(d_main, tmem_cross, a0, b_hi, b_lo, idesc, in_chunk > 0 ? 1u : 0u, slot > 0 ? 1u : 0u, bar_a_empty(as));
+            if (two) umma_f16a_slot(d_main, tmem_cross, a1, b_hi + 4, b_lo + 4, idesc, 1u, 1u, bar_a_empty(as1));
+          } else {
+            umma_f16x2_slot(d_main, tmem_cross, a0, b_hi, b_lo, idesc, in_chunk > 0 ? 1u : 0u, slot > 0 ? 1u : 0u, bar_a_empty(as));
+            if (two) umma_f16x2_slot(d_main, tmem_cross, a1, b_hi + 4, b_lo + 4, idesc, 1u, 1u, bar_a_empty(as1));   // +64 B along K
+          }
           umma_commit_elect(bar_b_empty(bs), 1u);
           umma_commit_elect(bar_main_full(buf), end_chunk ? 1u : 0u);
           umma_commit_elect(bar_cross_full(xb), last ? 1u : 0u);
@@ -442,7 +448,9 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
     const int u4 = lane & 3, rsub = lane >> 2;
     const uint32_t total_items = (uint32_t)my_tiles * (uint32_t)p.num_slots;
     // row state of the tile the gather is currently in: rows 32q + 16g + rsub + 8h  (r = 2g + h)
-    const float* rbase[4];
+    using TA = typename std::conditional<A16, __half, float>::type;
+    const TA* x = reinterpret_cast<const TA*>(x_raw);
+    const TA* rbase[4];
     int riy[4], rix[4];
     uint32_t cur_tl = 0xffffffffu, cur_slot0 = 0;
     F16_TRACE_DECL
@@ -477,10 +485,16 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const bool ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h && (unsigned)(rix[r] + (int)kx) < (unsigned)p.w;
-          dst[r] = load_run8(ok ? rbase[r] + off : g_zero_run, WIDE);
-          // the same rows, 16 units (4 slots) further along the channels of this tap: what this set gathers next
-          if (p.prefetch && u4 == 0 && ok && cu + 16 < p.d_upt.d)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase[r] + off + 128));
+          if constexpr (A16) {
+            // 8 channels = 16 bytes of halfs; the four words are the packed (hi) operand pairs as they are
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(ok ? static_cast<const void*>(rbase[r] + off) : static_cast<const void*>(g_zero_run)));
+            dst[r].v[0] = __uint_as_float(t.x); dst[r].v[1] = __uint_as_float(t.y); dst[r].v[2] = __uint_as_float(t.z); dst[r].v[3] = __uint_as_float(t.w);
+          } else {
+            dst[r] = load_run8(ok ? reinterpret_cast<const float*>(rbase[r] + off) : g_zero_run, WIDE);
+            // the same rows, 16 units (4 slots) further along the channels of this tap: what this set gathers next
+            if (p.prefetch && u4 == 0 && ok && cu + 16 < p.d_upt.d)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase[r] + off + 128));
+          }
         }
       } else {
         // two adjacent taps (ky, 2*kxp) and (ky, 2*kxp + 1): with a pixel pitch of 4 floats they are 8 contiguous
@@ -494,8 +508,8 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
           const bool row_ok = uvalid && (unsigned)(riy[r] + (int)ky) < (unsigned)p.h;
           const bool ok0 = row_ok && (unsigned)(rix[r] + kx) < (unsigned)p.w;
           const bool ok1 = row_ok && (unsigned)(rix[r] + kx + 1) < (unsigned)p.w;
-          const float4 a = __ldg(reinterpret_cast<const float4*>(ok0 ? rbase[r] + off : g_zero_run));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(ok1 ? rbase[r] + off + 4 : g_zero_run));
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ok0 ? reinterpret_cast<const float*>(rbase[r] + off) : g_zero_run));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ok1 ? reinterpret_cast<const float*>(rbase[r] + off + 4) : g_zero_run));
           dst[r].v[0] = a.x; dst[r].v[1] = a.y; dst[r].v[2] = a.z; dst[r].v[3] = a.w;
           dst[r].v[4] = b.x; dst[r].v[5] = b.y; dst[r].v[6] = b.z; dst[r].v[7] = b.w;
         }
@@ -508,9 +522,16 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        uint32_t v[16];
         const Run8& r0 = src[2 * g];               // lane rsub
         const Run8& r1 = src[2 * g + 1];           // lane rsub + 8
+        if constexpr (A16) {
+          uint32_t h[8];
+          h[0] = __float_as_uint(r0.v[0]); h[1] = __float_as_uint(r0.v[1]); h[2] = __float_as_uint(r1.v[0]); h[3] = __float_as_uint(r1.v[1]);
+          h[4] = __float_as_uint(r0.v[2]); h[5] = __float_as_uint(r0.v[3]); h[6] = __float_as_uint(r1.v[2]); h[7] = __float_as_uint(r1.v[3]);
+          tmem_st_16x256b_x2(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, h);
+          continue;
+        }
+        uint32_t v[16];
         split_pair(r0.v[0], r0.v[1], v[0], v[8]);
         split_pair(r0.v[2], r0.v[3], v[1], v[9]);
         split_pair(r1.v[0], r1.v[1], v[2], v[10]);
@@ -608,6 +629,51 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
       // 128B-swizzled box layout TMA expects, STG_BLOCKS 32-column blocks per round.  chk turns NaN as soon
       // as one output is inf / NaN.
       const f32x2 zero2 = pack_f32x2(0.f, 0.f);
+      // which output tensor a 32-column block belongs to (segments start at multiples of 32 columns)
+      auto segment_of = [&](int nb, int& local) -> int {
+        int sg = -1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < p.nseg && nb >= p.seg_col0[i] && nb < p.seg_col0[i] + p.seg_cout[i]) { sg = i; local = nb - p.seg_col0[i]; }
+        return sg;
+      };
+      if constexpr (O16) {
+        // FP16 feature map out: a thread owns one output row (pixel) and writes its 32-column blocks as 64 contiguous
+        // bytes, straight from registers.  A value that does not fit FP16 raises the status word like a non-finite one
+        // (x * 2^112 * 1.001 overflows to inf from |x| >= 65471).
+        const int m = m0 + 32 * q + lane;
+        const f32x2 big = pack_f32x2(5.1974e33f, 5.1974e33f);
+#pragma unroll
+        for (int qb = 0; qb < BLOCK_N / 32; ++qb) {
+          int local = 0;
+          const int sg = segment_of(n0 + qb * 32, local);
+          uint32_t hw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 u = unpack_f32x2(acc[qb * 16 + j]);
+            const float o0 = fminf(fmaxf(u.x, act_lo), act_hi), o1 = fminf(fmaxf(u.y, act_lo), act_hi);
+            chk = fma2(mul2(pack_f32x2(o0, o1), big), zero2, chk);
+            const __half2 h = __floats2half2_rn(o0, o1);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          if (sg < 0 || m >= p.M) continue;
+          __half* dst = reinterpret_cast<__half*>(p.seg_y[sg]) + (long long)(row_off + m) * p.seg_yld[sg] + local;
+          const int ncols = min(32, p.seg_cout[sg] - local);
+          if (ncols == 32 && p.tma_store) {                 // (tma_store: every y 16-byte aligned with an aligned pitch)
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4)
+              *reinterpret_cast<uint4*>(dst + v4 * 8) = make_uint4(hw[v4 * 4], hw[v4 * 4 + 1], hw[v4 * 4 + 2], hw[v4 * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h = *reinterpret_cast<const __half2*>(&hw[j]);
+              if (2 * j < ncols) dst[2 * j] = __low2half(h);
+              if (2 * j + 1 < ncols) dst[2 * j + 1] = __high2half(h);
+            }
+          }
+        }
+        continue;                                            // next tile
+      }
 #pragma unroll
       for (int round = 0; round < (BLOCK_N / 32) / L::STG_BLOCKS; ++round) {
         F16_TIMED(2, tma_store_wait_read());                     // this thread's earlier stores have read the staging buffer
@@ -627,14 +693,6 @@ conv_f16x2_kernel(const Params p, const float* __restrict__ x, const float* __re
             *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
           }
         }
-        // which output tensor a 32-column block belongs to (segments start at multiples of 32 columns)
-        auto segment_of = [&](int nb, int& local) -> int {
-          int sg = -1;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            if (i < p.nseg && nb >= p.seg_col0[i] && nb < p.seg_col0[i] + p.seg_cout[i]) { sg = i; local = nb - p.seg_col0[i]; }
-          return sg;
-        };
         if (p.tma_store) {
           fence_proxy_async();
           __syncwarp();
@@ -746,11 +804,11 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
   return B200OV_OK;
 }
 
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR>
-static int launch(const Params& p, const float* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16>
+static int launch(const Params& p, const void* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
                   const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s) {
   using L = Smem<BLOCK_N, SB>;
-  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR, A16, O16>;
   static bool configured = false;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -803,7 +861,9 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
 // The gather reads 8-float runs: either cin is a multiple of 8 (a run = 8 channels of one tap), or cin <= 4 with a
 // pixel pitch of exactly 4 floats (a run = two adjacent taps; the producer of x zero-fills the pad lanes, e.g. the
 // network-input layout kernel writes a 3-channel image with pitch 4).
-bool f16x2_eligible(const b200ov_conv_desc* d, const float* x) {
+bool f16x2_eligible(const b200ov_conv_desc* d, const void* x) {
+  if (d->x_dtype == B200OV_DT_F16)     // FP16 feature map in: 8-channel runs of 16 bytes
+    return (d->x_ld % 8 == 0) && aligned16(x) && d->cin % 8 == 0 && d->act != B200OV_ACT_SIGMOID;
   return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || (d->cin <= 4 && d->x_ld == 4)) &&
          d->act != B200OV_ACT_SIGMOID;
 }
@@ -849,8 +909,9 @@ int f16x2_splitk_plan(int m, int cout, int cin, int kh, int kw, int* ws_rows, in
   return ksplit;
 }
 
-int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, int nseg,
+int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, int nseg,
                        const b200ov_conv_seg* segs, cudaStream_t s, int ksplit, int ws_rows) {
+  const bool a16 = d->x_dtype == B200OV_DT_F16, o16 = d->y_dtype == B200OV_DT_F16;
   if (!f16x2_eligible(d, x))
     return set_error(B200OV_ERR_UNSUPPORTED, "f16x2 path needs 16-byte aligned NHWC input with cin %% 8 == 0 (or cin <= 4 at a pixel pitch of 4) and no fused Sigmoid");
   if (nseg < 1 || nseg > 3) return set_error(B200OV_ERR_INVALID, "conv2d: 1..3 output segments");
@@ -869,7 +930,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
         segs[i].y_ld < segs[i].cout)
       return set_error(B200OV_ERR_INVALID, "conv2d: bad output segment %d", i);
     p.seg_col0[i] = segs[i].col0; p.seg_cout[i] = segs[i].cout; p.seg_yld[i] = segs[i].y_ld; p.seg_y[i] = static_cast<float*>(segs[i].y);
-    if (segs[i].y_ld % 4 != 0 || !aligned16(segs[i].y)) p.tma_store = 0;
+    if (segs[i].y_ld % (o16 ? 8 : 4) != 0 || !aligned16(segs[i].y)) p.tma_store = 0;     // (FP16 out: "vector stores allowed")
   }
   int coutp, kpad, upt, units;
   f16_weight_dims(d->cout, d->cin, d->kh, d->kw, &coutp, &kpad, &upt, &units);
@@ -877,7 +938,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   p.num_slots = ceil_div(units, 4);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > 1) {
-    if (nseg != 1 || bias != nullptr || d->act != B200OV_ACT_NONE || ws_rows < (int)M)
+    if (nseg != 1 || bias != nullptr || d->act != B200OV_ACT_NONE || ws_rows < (int)M || o16)
       return set_error(B200OV_ERR_INVALID, "conv2d: split-K writes raw partial sums of one tensor (no bias / activation)");
     p.num_slots = round_up(ceil_div(p.num_slots, ksplit), 2);     // whole weight stages; the last split's tail reads zeros
   }
@@ -896,7 +957,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
   p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
-  p.pair4 = d->cin <= 4;
+  p.pair4 = d->cin <= 4 && !a16;
   const __half* hi_plane = reinterpret_cast<const __half*>(wt);
   int kw_eff = d->kw;
   if (p.pair4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0) {
@@ -916,7 +977,8 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
   // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1.
   { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
-  p.wide_loads = !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
+  p.wide_loads = !a16 && !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
+  if (a16) p.prefetch = 0;
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
   p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots); p.d_ksplit = FastDiv(ksplit);
   const __half* lo_plane = hi_plane + (long long)coutp * kpad;
@@ -926,7 +988,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
   rc = f16::make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo_plane, kpad, coutp, (long long)kpad * 2, f16::STAGE_K, block_n);
   if (rc) return rc;
   for (int i = 0; i < 3; ++i) {
-    if (p.tma_store && i < nseg) {
+    if (p.tma_store && i < nseg && !o16) {
       rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, segs[i].cout,
                             ksplit > 1 ? (long long)ksplit * ws_rows : (long long)p.M, (long long)segs[i].y_ld * 4, 32, 32);
       if (rc) return rc;
@@ -935,18 +997,22 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const float* x, const float* w
     }
   }
   unsigned int* status = f16x2_status_word();
+#define B200OV_F16_LAUNCH2(N_, SB_, W_, P_, A_) \
+  (o16 ? f16::launch<N_, SB_, W_, P_, A_, true>(p, x, bias, status, mh, ml, my, s) \
+       : f16::launch<N_, SB_, W_, P_, A_, false>(p, x, bias, status, mh, ml, my, s))
 #define B200OV_F16_LAUNCH(N_, SB_) \
-  (p.pair4 ? f16::launch<N_, SB_, false, true>(p, x, bias, status, mh, ml, my, s) \
-           : p.wide_loads ? f16::launch<N_, SB_, true, false>(p, x, bias, status, mh, ml, my, s) \
-                          : f16::launch<N_, SB_, false, false>(p, x, bias, status, mh, ml, my, s))
+  (a16 ? B200OV_F16_LAUNCH2(N_, SB_, false, false, true) \
+       : p.pair4 ? B200OV_F16_LAUNCH2(N_, SB_, false, true, false) \
+                 : p.wide_loads ? B200OV_F16_LAUNCH2(N_, SB_, true, false, false) : B200OV_F16_LAUNCH2(N_, SB_, false, false, false))
   if (block_n == 128) return B200OV_F16_LAUNCH(128, 4);
   if (block_n == 96) return B200OV_F16_LAUNCH(96, 4);
   if (block_n == 64) return B200OV_F16_LAUNCH(64, 6);
   return B200OV_F16_LAUNCH(32, 6);
 #undef B200OV_F16_LAUNCH
+#undef B200OV_F16_LAUNCH2
 }
 
-int conv2d_f16x2(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, cudaStream_t s) {
+int conv2d_f16x2(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, void* y, cudaStream_t s) {
   b200ov_conv_seg seg;
   seg.y = y; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = d->y_ld;
   return conv2d_f16x2_multi(d, x, wt, bias, 1, &seg, s, 1, 0);
@@ -978,7 +1044,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const float* x, const float* wt, const float* bias, float* y, float* ws,
+int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, float* y, float* ws,
                         size_t ws_bytes, cudaStream_t s) {
   int ws_rows, ws_ld;
   const long long M = (long long)d->n * d->oh * d->ow;

@@ -12,6 +12,7 @@
 #include "fastdiv.cuh"
 #include "tc_ptx.cuh"
 #include "tma_util.cuh"
+#include "vec4io.cuh"
 
 namespace b200ov {
 
@@ -188,7 +189,7 @@ struct DwTmaP {
   int n, c, oh, ow, y_ld;
   int pt, pl;
   int tw, tr, nimg, bw, bh;
-  int stage_bytes;
+  int stage_bytes, box_bytes;
   float lo, hi;
   uint32_t items;
   FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
@@ -196,10 +197,17 @@ struct DwTmaP {
 constexpr int DW_TMA_THREADS = 512;
 constexpr int DW_TMA_STAGES = 3;
 
-template <int S, int ACT>
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+template <int S, int ACT, typename T>
 __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const DwTmaP p, const __grid_constant__ CUtensorMap map_x,
                                                                          const float* __restrict__ wp, const float* __restrict__ bias,
-                                                                         float* __restrict__ y) {
+                                                                         T* __restrict__ y) {
+  using IO = Vec4IO<T>;
   using namespace ptx;
   extern __shared__ uint8_t dw_smem_raw[];
   const uint32_t base = (smem_u32(dw_smem_raw) + 127u) & ~127u;
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
     int cc, ct, rt, ig;
     decode(k, cc, ct, rt, ig);
     const uint32_t s = k % DW_TMA_STAGES;
-    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.stage_bytes);
+    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.box_bytes);
     tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
   };
   if (tid == 0)
@@ -258,19 +266,26 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
     }
     mbar_wait(bars + 8 * s, (k / DW_TMA_STAGES) & 1);
     if (active) {
-      const float* tile = reinterpret_cast<const float*>(base_ptr + s * p.stage_bytes) +
-                          ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
+      const T* tile = reinterpret_cast<const T*>(base_ptr + s * p.stage_bytes) +
+                      ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
       auto load_row = [&](int lr, ulonglong2 (&dst)[3]) {
-        const float* rp = tile + (size_t)lr * p.bw * 32;
+        const T* rp = tile + (size_t)lr * p.bw * 32;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) dst[kx] = *reinterpret_cast<const ulonglong2*>(rp + kx * 32);
+        for (int kx = 0; kx < 3; ++kx) {
+          if constexpr (sizeof(T) == 4) {
+            dst[kx] = *reinterpret_cast<const ulonglong2*>(rp + kx * 32);
+          } else {
+            const float4 v = IO::ld(rp + kx * 32);
+            dst[kx] = make_ulonglong2(pack2(v.x, v.y), pack2(v.z, v.w));
+          }
+        }
       };
       ulonglong2 R[3][3];
       constexpr int KEEP = 3 - S;                           // 2 (stride 1) or 1 (stride 2)
 #pragma unroll
       for (int i = 0; i < KEEP; ++i) load_row(r_begin * S + i, R[i]);
       const int oy0 = rt * p.tr;
-      float* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
+      T* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
       const size_t yrow = (size_t)p.ow * p.y_ld;
       for (int r = r_begin; r < r_end && oy0 + r < p.oh; ++r) {
 #pragma unroll
@@ -284,8 +299,8 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
             hi = fma2(R[ky][kx].y, wt[ky * 3 + kx].y, hi);
           }
         const float2 a = unpack2(lo), b = unpack2(hi);
-        *reinterpret_cast<float4*>(yp) = make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi),
-                                                     act_t<ACT>(b.x, p.lo, p.hi), act_t<ACT>(b.y, p.lo, p.hi));
+        IO::st(yp, make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
+                               act_t<ACT>(b.y, p.lo, p.hi)));
         yp += yrow;
 #pragma unroll
         for (int i = 0; i < KEEP; ++i)
@@ -297,8 +312,9 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
   }
 }
 
-static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q) {
+static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q, int esize) {
   const int K = 3, S = d->sh;
+  const int cb = 32 * esize;
   const int col_tiles = ceil_div(d->ow, 32);
   q.tw = ceil_div(d->ow, col_tiles);
   q.nimg = 32 / q.tw;
@@ -307,16 +323,17 @@ static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q) {
   q.bw = (q.tw - 1) * S + K;
   const int budget = 64 * 1024;
   int tr = d->oh;
-  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
-  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) {
+  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
+  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {
     q.nimg = 1;
     tr = d->oh;
-    while (tr > 1 && ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+    while (tr > 1 && ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
   }
   const int row_tiles = ceil_div(d->oh, tr);
   q.tr = ceil_div(d->oh, row_tiles);
   q.bh = (q.tr - 1) * S + K;
-  q.stage_bytes = q.nimg * q.bh * q.bw * 128;
+  q.box_bytes = q.nimg * q.bh * q.bw * cb;
+  q.stage_bytes = round_up(q.box_bytes, 128);
   if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
   const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
@@ -328,9 +345,9 @@ static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q) {
   return true;
 }
 
-template <int S, int ACT>
-static int launch_dw_tma(const DwTmaP& q, const CUtensorMap& map, const float* wp, const float* bias, float* y, cudaStream_t s) {
-  auto kern = dwconv3x3_tma_kernel<S, ACT>;
+template <int S, int ACT, typename T>
+static int launch_dw_tma(const DwTmaP& q, const CUtensorMap& map, const float* wp, const float* bias, T* y, cudaStream_t s) {
+  auto kern = dwconv3x3_tma_kernel<S, ACT, T>;
   static bool configured = false;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * 72 * 1024 + 8 * DW_TMA_STAGES + 256));
@@ -453,8 +470,10 @@ int b200ov_pack_dw_weights(const float* w_g11hw, float* w_packed, int c, int kh,
   return B200OV_OK;
 }
 
-int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_packed, const float* bias, float* y,
+int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const void* x_raw, const float* w_packed, const float* bias, void* y_raw,
                     void* stream) {
+  const float* x = static_cast<const float*>(x_raw);
+  float* y = static_cast<float*>(y_raw);
   B200OV_REQUIRE(d && x && w_packed && y, "dwconv2d: null argument");
   B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 &&
                      d->oh > 0 && d->ow > 0 && d->pt >= 0 && d->pl >= 0,
@@ -469,13 +488,37 @@ int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const float* x, const float* w_
                    aligned16(w_packed) && (bias == nullptr || aligned16(bias));
   const int V = vec ? 4 : 1;
   const int cg = d->c / V;
+  B200OV_REQUIRE(d->dtype == B200OV_DT_F32 || d->dtype == B200OV_DT_F16, "dwconv2d: bad storage type");
+  if (d->dtype == B200OV_DT_F16) {
+    // FP16 feature maps: the TMA tile kernel only (3x3, stride 1 / 2, packed-FMA arithmetic)
+    const bool ok = d->c % 4 == 0 && d->x_ld % 8 == 0 && d->y_ld % 4 == 0 && aligned16(x_raw) && aligned_vec4<__half>(y_raw) &&
+                    aligned16(w_packed) && (bias == nullptr || aligned16(bias)) && d->math != B200OV_DW_EXACT && d->kh == 3 &&
+                    d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2) && d->act <= B200OV_ACT_CLAMP;
+    DwTmaP tq;
+    CUtensorMap map;
+    if (!ok || !dw_tma_plan(d, tq, 2) ||
+        tma::make_map_nhwc(&map, x_raw, 2, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) != B200OV_OK)
+      return set_error(B200OV_ERR_UNSUPPORTED, "dwconv2d: this shape has no FP16-storage kernel");
+    __half* yh = static_cast<__half*>(y_raw);
+#define B200OV_DWH(S_, A_) return launch_dw_tma<S_, A_, __half>(tq, map, w_packed, bias, yh, s)
+    if (d->sh == 1) {
+      if (d->act == B200OV_ACT_NONE) B200OV_DWH(1, B200OV_ACT_NONE);
+      if (d->act == B200OV_ACT_RELU) B200OV_DWH(1, B200OV_ACT_RELU);
+      B200OV_DWH(1, B200OV_ACT_CLAMP);
+    } else {
+      if (d->act == B200OV_ACT_NONE) B200OV_DWH(2, B200OV_ACT_NONE);
+      if (d->act == B200OV_ACT_RELU) B200OV_DWH(2, B200OV_ACT_RELU);
+      B200OV_DWH(2, B200OV_ACT_CLAMP);
+    }
+#undef B200OV_DWH
+  }
   const bool hot = vec && d->math != B200OV_DW_EXACT && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2);
   static const bool no_tma = getenv("B200OV_DW_NO_TMA") != nullptr && atoi(getenv("B200OV_DW_NO_TMA")) != 0;     // developer knob (A/B)
   if (hot && !no_tma && d->act <= B200OV_ACT_CLAMP && (long long)d->n * d->oh * d->ow * d->c >= (1 << 16)) {
     DwTmaP tq;
     CUtensorMap map;
-    if (dw_tma_plan(d, tq) && tma::make_map_nhwc(&map, x, 4, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
-#define B200OV_DWT(S_, A_) return launch_dw_tma<S_, A_>(tq, map, w_packed, bias, y, s)
+    if (dw_tma_plan(d, tq, 4) && tma::make_map_nhwc(&map, x, 4, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
+#define B200OV_DWT(S_, A_) return launch_dw_tma<S_, A_, float>(tq, map, w_packed, bias, y, s)
       if (d->sh == 1) {
         if (d->act == B200OV_ACT_NONE) B200OV_DWT(1, B200OV_ACT_NONE);
         if (d->act == B200OV_ACT_RELU) B200OV_DWT(1, B200OV_ACT_RELU);

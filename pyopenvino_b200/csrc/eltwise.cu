@@ -9,6 +9,7 @@
 //  lrn        : LRN.py:10-22 across channels (contiguous in NHWC), alpha not divided by size.
 #include "common.cuh"
 #include "fastdiv.cuh"
+#include "vec4io.cuh"
 
 namespace b200ov {
 
@@ -136,8 +137,8 @@ __device__ __forceinline__ float lrn_pow(float v, float beta) { return powf(v, b
 // Vector form: a thread owns 4 consecutive channels of one pixel and reads the neighbouring float4s
 // for the window (half <= 4), i.e. 3 128-bit loads per 4 outputs instead of 4 * (2*half + 2) scalar loads.
 // HALF > 0: compile-time half-window; HALF = 0: runtime `half`.
-template <int HALF>
-__global__ void __launch_bounds__(256) lrn_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t total,
+template <int HALF, typename T = float>
+__global__ void __launch_bounds__(256) lrn_vec4_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t total,
                                                        FastDiv d_cg, int x_ld, int y_ld, int half_rt, float alpha,
                                                        float beta, float bias) {
   const int half = HALF > 0 ? HALF : half_rt;
@@ -147,11 +148,11 @@ __global__ void __launch_bounds__(256) lrn_vec4_kernel(const float* __restrict__
     uint32_t pix, gu;
     d_cg.divmod(idx, pix, gu);
     const int g = (int)gu;
-    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)pix * x_ld) + g;
+    const T* xp = x + (size_t)pix * x_ld + 4 * g;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 cur = __ldg(xp);
-    const float4 prv = g > 0 ? __ldg(xp - 1) : zero;
-    const float4 nxt = g + 1 < cg ? __ldg(xp + 1) : zero;
+    const float4 cur = Vec4IO<T>::ldg(xp);
+    const float4 prv = g > 0 ? Vec4IO<T>::ldg(xp - 4) : zero;
+    const float4 nxt = g + 1 < cg ? Vec4IO<T>::ldg(xp + 4) : zero;
     const float v[12] = {prv.x, prv.y, prv.z, prv.w, cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
     float sq[12];
 #pragma unroll
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) lrn_vec4_kernel(const float* __restrict__
         if (d >= -half && d <= half) s = __fadd_rn(s, sq[4 + j + d]);
       o[j] = lrn_scale(v[4 + j], __fadd_rn(bias, __fmul_rn(alpha, s)), beta);
     }
-    *reinterpret_cast<float4*>(y + (size_t)pix * y_ld + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+    Vec4IO<T>::st(y + (size_t)pix * y_ld + 4 * g, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
@@ -220,6 +221,28 @@ int b200ov_softmax(const float* x, float* y, int rows, int cols, void* stream) {
   if (rows == 0) return B200OV_OK;
   softmax_kernel<<<rows, 128, 0, as_stream(stream)>>>(x, y, cols);
   B200OV_LAUNCH_CHECK("softmax_kernel");
+  return B200OV_OK;
+}
+
+int b200ov_lrn_st(const void* x, void* y, int dtype, int64_t pixels, int c, int x_ld, int y_ld, int size, float alpha, float beta,
+                  float bias, void* stream) {
+  if (dtype == B200OV_DT_F32)
+    return b200ov_lrn(static_cast<const float*>(x), static_cast<float*>(y), pixels, c, x_ld, y_ld, size, alpha, beta, bias, stream);
+  B200OV_REQUIRE(dtype == B200OV_DT_F16, "lrn: bad storage type");
+  B200OV_REQUIRE(x && y && pixels >= 0 && c > 0 && x_ld >= c && y_ld >= c && size > 0, "lrn: bad argument");
+  if (pixels == 0) return B200OV_OK;
+  const long long items = pixels * (c / 4);
+  if (!((c % 4 == 0) && (x_ld % 4 == 0) && (y_ld % 4 == 0) && aligned_vec4<__half>(x) && aligned_vec4<__half>(y) && size / 2 <= 4 &&
+        items < 0x7fffffffLL))
+    return set_error(B200OV_ERR_UNSUPPORTED, "lrn: this shape has no FP16-storage kernel");
+  const int g = bw_grid(items, 256);
+  const __half* xh = static_cast<const __half*>(x);
+  __half* yh = static_cast<__half*>(y);
+  if (size / 2 == 2)
+    lrn_vec4_kernel<2, __half><<<g, 256, 0, as_stream(stream)>>>(xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, 2, alpha, beta, bias);
+  else
+    lrn_vec4_kernel<0, __half><<<g, 256, 0, as_stream(stream)>>>(xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, size / 2, alpha, beta, bias);
+  B200OV_LAUNCH_CHECK("lrn_kernel");
   return B200OV_OK;
 }
 

@@ -17,11 +17,13 @@ __device__ __forceinline__ float widen(uint8_t v) { return (float)v; }
 __device__ __forceinline__ float widen(int8_t v) { return (float)v; }
 template <typename T>
 __device__ __forceinline__ float load_widen(const T* p) { return widen(__ldg(p)); }
+__device__ __forceinline__ void store_narrow(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_narrow(__half* p, float v) { *p = __float2half_rn(v); }
 
 // x: [batch][rows][x_ld] (cols valid)  ->  y: [batch][cols][y_ld] (rows valid)
 // AFFINE: v = v*scale[row] + shift[row] (row = source row = channel of an NCHW tensor)
-template <bool AFFINE, typename TIN = float>
-__global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ x, float* __restrict__ y, int rows,
+template <bool AFFINE, typename TIN = float, typename TOUT = float>
+__global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ x, TOUT* __restrict__ y, int rows,
                                                         int cols, int x_ld, int y_ld, int tiles_r, int tiles_c,
                                                         int has_scale, const float* __restrict__ scale_vec,
                                                         float scale_s, int has_shift,
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ 
   const int tr = (int)(bid % tiles_r);
   const int b = (int)(bid / tiles_r);
   const TIN* xb = x + (long long)b * rows * x_ld;
-  float* yb = y + (long long)b * cols * y_ld;
+  TOUT* yb = y + (long long)b * cols * y_ld;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     int c = tc * 32 + ty + i, r = tr * 32 + tx;
-    if (r < rows && c < cols) yb[(long long)c * y_ld + r] = tile[tx][ty + i];
+    if (r < rows && c < cols) store_narrow(yb + (long long)c * y_ld + r, tile[tx][ty + i]);
   }
 }
 
@@ -158,6 +160,30 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
   }
 }
 
+template <typename TIN, typename TOUT>
+__global__ void __launch_bounds__(256) copy2d_cast_kernel(const TIN* __restrict__ src, TOUT* __restrict__ dst, long long rows, int cols,
+                                                          int src_ld, int dst_ld) {
+  // two elements per thread where the row pitch allows (cols, src_ld, dst_ld even): 32-bit / 64-bit accesses
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    store_narrow(dst + r * dst_ld + c, load_widen(src + r * src_ld + c));
+  }
+}
+
+template <typename TIN, typename TOUT>
+static int launch_transpose_st(const TIN* x, TOUT* y, int batch, int rows, int cols, int x_ld, int y_ld, cudaStream_t s) {
+  const int tiles_r = ceil_div(rows, 32), tiles_c = ceil_div(cols, 32);
+  const long long blocks = (long long)batch * tiles_r * tiles_c;
+  if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "transpose: grid too large");
+  if (blocks == 0) return B200OV_OK;
+  transpose_kernel<false, TIN, TOUT><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr, 0.f, 0,
+                                                                     nullptr, 0.f);
+  B200OV_LAUNCH_CHECK("transpose_kernel");
+  return B200OV_OK;
+}
+
 static int launch_transpose(bool affine, const float* x, float* y, int batch, int rows, int cols, int x_ld, int y_ld,
                             int has_scale, const float* scale_vec, float scale_s, int has_shift,
                             const float* shift_vec, float shift_s, cudaStream_t s) {
@@ -255,6 +281,37 @@ int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int h
       return input_to_nhwc_typed(static_cast<const float*>(x), y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift,
                                  shift_vec, shift_s, as_stream(stream));
   }
+}
+
+int b200ov_transpose_st(const void* x, int x_dtype, void* y, int y_dtype, int batch, int rows, int cols, int x_ld, int y_ld,
+                        void* stream) {
+  B200OV_REQUIRE(x && y && batch >= 0 && rows > 0 && cols > 0 && x_ld >= cols && y_ld >= rows, "transpose: bad argument");
+  cudaStream_t s = as_stream(stream);
+  const bool xh = x_dtype == B200OV_DT_F16, yh = y_dtype == B200OV_DT_F16;
+  B200OV_REQUIRE((xh || x_dtype == B200OV_DT_F32) && (yh || y_dtype == B200OV_DT_F32), "transpose: bad storage type");
+  if (xh && yh) return launch_transpose_st(static_cast<const __half*>(x), static_cast<__half*>(y), batch, rows, cols, x_ld, y_ld, s);
+  if (xh) return launch_transpose_st(static_cast<const __half*>(x), static_cast<float*>(y), batch, rows, cols, x_ld, y_ld, s);
+  if (yh) return launch_transpose_st(static_cast<const float*>(x), static_cast<__half*>(y), batch, rows, cols, x_ld, y_ld, s);
+  return launch_transpose_st(static_cast<const float*>(x), static_cast<float*>(y), batch, rows, cols, x_ld, y_ld, s);
+}
+
+int b200ov_copy2d_st(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t rows, int cols, int src_ld, int dst_ld,
+                     void* stream) {
+  B200OV_REQUIRE(src && dst && rows >= 0 && cols > 0 && src_ld >= cols && dst_ld >= cols, "copy2d: bad argument");
+  const bool sh = src_dtype == B200OV_DT_F16, dh = dst_dtype == B200OV_DT_F16;
+  B200OV_REQUIRE((sh || src_dtype == B200OV_DT_F32) && (dh || dst_dtype == B200OV_DT_F32), "copy2d: bad storage type");
+  if (rows == 0) return B200OV_OK;
+  if (!sh && !dh) return b200ov_copy2d(static_cast<const float*>(src), static_cast<float*>(dst), rows, cols, src_ld, dst_ld, stream);
+  cudaStream_t s = as_stream(stream);
+  if (sh && dh && cols % 2 == 0 && src_ld % 2 == 0 && dst_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 3u) == 0)       // half -> half: a float copy of half the width
+    return b200ov_copy2d(static_cast<const float*>(src), static_cast<float*>(dst), rows, cols / 2, src_ld / 2, dst_ld / 2, stream);
+  const int g = bw_grid(rows * cols, 256);
+  if (sh && dh) copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
+  else if (sh) copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(src), static_cast<float*>(dst), rows, cols, src_ld, dst_ld);
+  else copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
+  B200OV_LAUNCH_CHECK("copy2d_cast_kernel");
+  return B200OV_OK;
 }
 
 int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream) {

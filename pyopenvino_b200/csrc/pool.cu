@@ -19,6 +19,7 @@
 #include "fastdiv.cuh"
 #include "tc_ptx.cuh"
 #include "tma_util.cuh"
+#include "vec4io.cuh"
 
 namespace b200ov {
 
@@ -151,7 +152,7 @@ struct PoolTmaP {
   int n, c, oh, ow, y_ld;
   int pt, pl, hp, wpad;
   int tw, tr, nimg, bw, bh;
-  int stage_bytes;
+  int stage_bytes, box_bytes;
   uint32_t items;
   FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
 };
@@ -159,10 +160,11 @@ struct PoolTmaP {
 constexpr int POOL_TMA_THREADS = 512;
 constexpr int POOL_TMA_STAGES = 3;
 
-template <int K, int S>
+template <int K, int S, typename T>
 __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const PoolTmaP p, const __grid_constant__ CUtensorMap map_x,
                                                                           const float* __restrict__ scale,
-                                                                          const float* __restrict__ shift, float* __restrict__ y) {
+                                                                          const float* __restrict__ shift, T* __restrict__ y) {
+  using IO = Vec4IO<T>;
   using namespace ptx;
   extern __shared__ uint8_t pool_smem_raw[];
   const uint32_t base = (smem_u32(pool_smem_raw) + 127u) & ~127u;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
     int cc, ct, rt, ig;
     decode(k, cc, ct, rt, ig);
     const uint32_t s = k % POOL_TMA_STAGES;
-    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.stage_bytes);
+    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.box_bytes);
     tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
   };
   if (tid == 0)
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
     const int img = ig * p.nimg + (int)img_l;
     const int ox = ct * p.tw + (int)ox_l;
     if (lane_ok && img < p.n && ox < p.ow && c0 < p.c && (int)ox_l < p.tw) {
-      const float* tile = reinterpret_cast<const float*>(base_ptr + s * p.stage_bytes) +
-                          ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
+      const T* tile = reinterpret_cast<const T*>(base_ptr + s * p.stage_bytes) +
+                      ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
       bool col_ok[K];
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) col_ok[kx] = ox * S + kx < p.wpad;
@@ -227,11 +229,11 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
       // horizontal maximum of tile row `lr` (padded row oy0*S + lr); -inf when the row lies beyond the padded tensor
       auto hmax = [&](int lr) -> float4 {
         if (oy0 * S + lr >= p.hp) return ninf;
-        const float* rp = tile + (size_t)lr * p.bw * 32;
+        const T* rp = tile + (size_t)lr * p.bw * 32;
         float4 m = ninf;
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          const float4 v = *reinterpret_cast<const float4*>(rp + kx * 32);
+          const float4 v = IO::ld(rp + kx * 32);
           if (col_ok[kx]) m = max4(m, v);
         }
         return m;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
       float4 keep[KEEP > 0 ? KEEP : 1];
 #pragma unroll
       for (int i = 0; i < KEEP; ++i) keep[i] = hmax(r_begin * S + i);
-      float* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
+      T* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
       const size_t yrow = (size_t)p.ow * p.y_ld;
       for (int r = r_begin; r < r_end && oy0 + r < p.oh; ++r) {
         float4 o = ninf;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
         }
         if (scale != nullptr) { o.x = __fmul_rn(o.x, sc.x); o.y = __fmul_rn(o.y, sc.y); o.z = __fmul_rn(o.z, sc.z); o.w = __fmul_rn(o.w, sc.w); }
         if (shift != nullptr) { o.x = __fadd_rn(o.x, sf.x); o.y = __fadd_rn(o.y, sf.y); o.z = __fadd_rn(o.z, sf.z); o.w = __fadd_rn(o.w, sf.w); }
-        *reinterpret_cast<float4*>(yp) = o;
+        IO::st(yp, o);
         yp += yrow;
       }
     }
@@ -268,8 +270,9 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
 }
 
 // Tile geometry for the TMA kernel; false when the shape does not fit (the strip / generic kernels take over).
-static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q) {
+static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q, int esize) {
   const int K = d->kh, S = d->sh;
+  const int cb = 32 * esize;                      // bytes of one pixel's 32-channel chunk
   if (d->ow <= 0 || d->oh <= 0) return false;
   const int col_tiles = ceil_div(d->ow, 32);
   q.tw = ceil_div(d->ow, col_tiles);
@@ -279,16 +282,17 @@ static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q) {
   q.bw = (q.tw - 1) * S + K;
   const int budget = 64 * 1024;
   int tr = d->oh;
-  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
-  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * 128 > budget) {       // several images do not fit even one row
+  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
+  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {       // several images do not fit even one row
     q.nimg = 1;
     tr = d->oh;
-    while (tr > 1 && ((tr - 1) * S + K) * q.bw * 128 > budget) --tr;
+    while (tr > 1 && ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
   }
   const int row_tiles = ceil_div(d->oh, tr);
   q.tr = ceil_div(d->oh, row_tiles);
   q.bh = (q.tr - 1) * S + K;
-  q.stage_bytes = q.nimg * q.bh * q.bw * 128;
+  q.box_bytes = q.nimg * q.bh * q.bw * cb;
+  q.stage_bytes = round_up(q.box_bytes, 128);
   if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
   const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
@@ -300,9 +304,9 @@ static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q) {
   return true;
 }
 
-template <int K, int S>
-static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const float* scale, const float* shift, float* y, cudaStream_t s) {
-  auto kern = pool_max_tma_kernel<K, S>;
+template <int K, int S, typename T>
+static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const float* scale, const float* shift, T* y, cudaStream_t s) {
+  auto kern = pool_max_tma_kernel<K, S, T>;
   static bool configured = false;
   const int smem = POOL_TMA_STAGES * 72 * 1024 + 8 * POOL_TMA_STAGES + 256;
   if (!configured) {
@@ -316,9 +320,24 @@ static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const floa
   return B200OV_OK;
 }
 
-template <int V>
-__global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restrict__ x, const float* __restrict__ scale,
-                                                   const float* __restrict__ shift, float* __restrict__ y) {
+template <int V, typename T>
+__device__ __forceinline__ void loadv_t(const T* p, float (&v)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = Vec4IO<T>::ldg(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = __ldg(reinterpret_cast<const float*>(p));
+  }
+}
+template <int V, typename T>
+__device__ __forceinline__ void storev_t(T* p, const float (&v)[V]) {
+  if constexpr (V == 4) Vec4IO<T>::st(p, make_float4(v[0], v[1], v[2], v[3]));
+  else *reinterpret_cast<float*>(p) = v[0];
+}
+
+template <int V, typename T = float>
+__global__ void __launch_bounds__(256) pool_kernel(PoolP p, const T* __restrict__ x, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, T* __restrict__ y) {
   const int cg = p.c / V;
   const long long total = (long long)p.n * p.oh * p.ow * cg;
   const int hp = p.h + p.pt + p.pb, wpad = p.w + p.pl + p.pr;
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restr
     const int oy = (int)(t % p.oh);
     const int img = (int)(t / p.oh);
     const int c0 = g * V;
-    const float* ximg = x + (long long)img * p.h * p.w * p.x_ld + c0;
+    const T* ximg = x + (long long)img * p.h * p.w * p.x_ld + c0;
     float res[V];
     if (p.mode == B200OV_POOL_MAX) {
 #pragma unroll
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restr
           const int ix = px - p.pl;
           float v[V];
           if (row_in && ix >= 0 && ix < p.w) {
-            loadv<V>(ximg + ((long long)iy * p.w + ix) * p.x_ld, v);
+            loadv_t<V, T>(ximg + ((long long)iy * p.w + ix) * p.x_ld, v);
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[j] = 0.f;   // the zero padding participates
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restr
       for (int iy = y0; iy < y1; ++iy)
         for (int ix = x0; ix < x1; ++ix) {
           float v[V];
-          loadv<V>(ximg + ((long long)iy * p.w + ix) * p.x_ld, v);
+          loadv_t<V, T>(ximg + ((long long)iy * p.w + ix) * p.x_ld, v);
 #pragma unroll
           for (int j = 0; j < V; ++j) res[j] = __fadd_rn(res[j], v[j]);
           ++cnt;
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restr
 #pragma unroll
       for (int j = 0; j < V; ++j) res[j] = __fadd_rn(res[j], s[j]);
     }
-    storev<V>(y + pix * p.y_ld + c0, res);
+    storev_t<V, T>(y + pix * p.y_ld + c0, res);
   }
 }
 
@@ -391,8 +410,33 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const float* __restr
 
 using namespace b200ov;
 
-extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const float* scale, const float* shift,
-                             float* y, void* stream) {
+// FP16 feature maps (d->dtype == B200OV_DT_F16): the TMA tile kernel for the MaxPool hot cases, the generic kernel otherwise
+static int pool2d_f16(const b200ov_pool_desc* d, const __half* x, const float* scale, const float* shift, __half* y, cudaStream_t s) {
+  const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned_vec4<__half>(x) && aligned_vec4<__half>(y) &&
+                   (scale == nullptr || aligned16(scale)) && (shift == nullptr || aligned16(shift));
+  if (!vec) return set_error(B200OV_ERR_UNSUPPORTED, "pool2d: FP16 feature maps need C %% 4 == 0 and 8-byte aligned pixels");
+  const bool hot = d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && d->sh == d->sw && (d->sh == 1 || d->sh == 2);
+  if (hot && d->x_ld % 8 == 0 && aligned16(x)) {
+    PoolTmaP tq;
+    CUtensorMap map;
+    if (pool_tma_plan(d, tq, 2) && tma::make_map_nhwc(&map, x, 2, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
+      if (d->kh == 3 && d->sh == 1) return launch_pool_tma<3, 1, __half>(tq, map, scale, shift, y, s);
+      if (d->kh == 3) return launch_pool_tma<3, 2, __half>(tq, map, scale, shift, y, s);
+      if (d->sh == 1) return launch_pool_tma<2, 1, __half>(tq, map, scale, shift, y, s);
+      return launch_pool_tma<2, 2, __half>(tq, map, scale, shift, y, s);
+    }
+  }
+  PoolP p{d->n, d->h, d->w, d->c, d->kh, d->kw, d->sh, d->sw, d->pt, d->pl, d->pb, d->pr, d->oh, d->ow, d->x_ld, d->y_ld, d->mode};
+  const long long total = (long long)d->n * d->oh * d->ow * (d->c / 4);
+  pool_kernel<4, __half><<<bw_grid(total, 256), 256, 0, s>>>(p, x, scale, shift, y);
+  B200OV_LAUNCH_CHECK("pool_kernel");
+  return B200OV_OK;
+}
+
+extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const void* x_raw, const float* scale, const float* shift,
+                             void* y_raw, void* stream) {
+  const float* x = static_cast<const float*>(x_raw);
+  float* y = static_cast<float*>(y_raw);
   B200OV_REQUIRE(d && x && y, "pool2d: null argument");
   B200OV_REQUIRE(d->n >= 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->kh > 0 && d->kw > 0 && d->sh > 0 && d->sw > 0 &&
                      d->oh > 0 && d->ow > 0 && d->pt >= 0 && d->pl >= 0 && d->pb >= 0 && d->pr >= 0,
@@ -405,6 +449,9 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   PoolP p{d->n, d->h, d->w, d->c, d->kh, d->kw, d->sh, d->sw, d->pt, d->pl, d->pb, d->pr, d->oh, d->ow, d->x_ld, d->y_ld,
           d->mode};
   if (d->n == 0) return B200OV_OK;
+  B200OV_REQUIRE(d->dtype == B200OV_DT_F32 || d->dtype == B200OV_DT_F16, "pool2d: bad storage type");
+  if (d->dtype == B200OV_DT_F16)
+    return pool2d_f16(d, static_cast<const __half*>(x_raw), scale, shift, static_cast<__half*>(y_raw), as_stream(stream));
   const bool vec = (d->c % 4 == 0) && (d->x_ld % 4 == 0) && (d->y_ld % 4 == 0) && aligned16(x) && aligned16(y) &&
                    (scale == nullptr || aligned16(scale)) && (shift == nullptr || aligned16(shift));
   const bool hot = vec && d->mode == B200OV_POOL_MAX && d->kh == d->kw && (d->kh == 2 || d->kh == 3) && d->sh == d->sw && (d->sh == 1 || d->sh == 2);
@@ -412,13 +459,13 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   if (hot && !no_tma && (long long)d->n * d->oh * d->ow * d->c >= (1 << 16)) {
     PoolTmaP tq;
     CUtensorMap map;
-    if (pool_tma_plan(d, tq) &&
+    if (pool_tma_plan(d, tq, 4) &&
         tma::make_map_nhwc(&map, x, 4, d->n, d->h, d->w, d->c, d->x_ld, 32, tq.bw, tq.bh, tq.nimg) == B200OV_OK) {
       cudaStream_t s = as_stream(stream);
-      if (d->kh == 3 && d->sh == 1) return launch_pool_tma<3, 1>(tq, map, scale, shift, y, s);
-      if (d->kh == 3) return launch_pool_tma<3, 2>(tq, map, scale, shift, y, s);
-      if (d->sh == 1) return launch_pool_tma<2, 1>(tq, map, scale, shift, y, s);
-      return launch_pool_tma<2, 2>(tq, map, scale, shift, y, s);
+      if (d->kh == 3 && d->sh == 1) return launch_pool_tma<3, 1, float>(tq, map, scale, shift, y, s);
+      if (d->kh == 3) return launch_pool_tma<3, 2, float>(tq, map, scale, shift, y, s);
+      if (d->sh == 1) return launch_pool_tma<2, 1, float>(tq, map, scale, shift, y, s);
+      return launch_pool_tma<2, 2, float>(tq, map, scale, shift, y, s);
     }
   }
   if (hot) {
@@ -445,8 +492,8 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const float* x, const fl
   }
   long long total = (long long)d->n * d->oh * d->ow * (vec ? d->c / 4 : d->c);
   int grid = bw_grid(total, 256);
-  if (vec) pool_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
-  else pool_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
+  if (vec) pool_kernel<4, float><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
+  else pool_kernel<1, float><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
   B200OV_LAUNCH_CHECK("pool_kernel");
   return B200OV_OK;
 }

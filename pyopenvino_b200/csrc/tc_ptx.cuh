@@ -123,6 +123,27 @@ __device__ __forceinline__ void umma_f16x2_slot(uint32_t d_main, uint32_t d_cros
       ::"r"(d_main), "r"(d_cross), "r"(a0), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_main), "r"(acc_cross), "r"(bar_a_empty)
       : "memory");
 }
+// The same for an A operand that already IS FP16 (feature maps stored as halfs): a = a_hi exactly, so the a_lo * w_hi
+// products vanish and a slot costs four MMAs (two K steps of a*w_hi -> main, a*w_lo -> cross) instead of six.
+__device__ __forceinline__ void umma_f16a_slot(uint32_t d_main, uint32_t d_cross, uint32_t a0, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t idesc, uint32_t acc_main, uint32_t acc_cross, uint32_t bar_a_empty) {
+  asm volatile(
+      "{\n\t.reg .pred pm, pc, le;\n\t.reg .b32 a8;\n\t.reg .b64 h2, l2;\n\t"
+      "setp.ne.b32 pm, %6, 0;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "elect.sync _|le, 0xffffffff;\n\t"
+      "add.u32 a8, %2, 8;\n\t"
+      "add.u64 h2, %3, 2;\n\t"
+      "add.u64 l2, %4, 2;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pm;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %4, %5, pc;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%0], [a8], h2, %5, 1;\n\t"
+      "@le tcgen05.mma.cta_group::1.kind::f16 [%1], [a8], l2, %5, 1;\n\t"
+      "@le tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}"
+      ::"r"(d_main), "r"(d_cross), "r"(a0), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_main), "r"(acc_cross), "r"(bar_a_empty)
+      : "memory");
+}
 // tcgen05.commit by one elected lane of a converged warp, if `cond` (warp-uniform) is non-zero
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar, uint32_t cond) {
   asm volatile(
@@ -155,6 +176,13 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// 16 lanes x 16 columns (two column blocks of 8): v[4j+0..1] = lane t/4, v[4j+2..3] = lane t/4 + 8 of block j
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -237,26 +237,40 @@ def alloc_f32(nfloats):
 
 
 class DeviceArray:
-    """float32 tensor resident in HBM.
+    """FP32 tensor of the graph, resident in HBM.
 
     layout 'plain': `t` holds prod(shape) floats, row-major in logical order.
-    layout 'nhwc' : logical shape (N, C, H, W); `t` holds N*H*W*ld floats; this array's channels are
+    layout 'nhwc' : logical shape (N, C, H, W); `t` holds N*H*W*ld elements; this array's channels are
                     [c_off, c_off + C) of each pixel.
+    `st` is the STORAGE type of an 'nhwc' feature map: 'f32' (default, the reference's precision) or 'f16' (opt-in
+    storage mode, `load_network(..., storage='f16')`: half the bytes, every kernel still computes in FP32).  The logical
+    `dtype` the plugin contract validates stays float32 either way; `t` is always a float32 torch tensor used as raw
+    storage (an 'f16' map of n elements occupies ceil(n / 2) of its floats).
     """
-    __slots__ = ('t', 'shape', 'layout', 'ld', 'c_off', 'cache')
+    __slots__ = ('t', 'shape', 'layout', 'ld', 'c_off', 'cache', 'st')
     dtype = np.dtype(np.float32)
 
-    def __init__(self, t, shape, layout='plain', ld=None, c_off=0):
+    def __init__(self, t, shape, layout='plain', ld=None, c_off=0, st='f32'):
         self.t = t
         self.shape = tuple(int(s) for s in shape)
         self.layout = layout
         self.ld = int(ld) if ld is not None else (self.shape[1] if layout == 'nhwc' else 0)
         self.c_off = int(c_off)
         self.cache = {}
+        self.st = st
+        assert st == 'f32' or layout == 'nhwc'
+
+    @property
+    def esize(self):
+        return 2 if self.st == 'f16' else 4
+
+    @property
+    def code(self):
+        return _cabi.DT_F16 if self.st == 'f16' else _cabi.DT_F32
 
     @property
     def ptr(self):
-        return self.t.data_ptr() + 4 * self.c_off
+        return self.t.data_ptr() + self.esize * self.c_off
 
     @property
     def ndim(self):
@@ -290,7 +304,7 @@ class DeviceArray:
         return a.astype(dtype) if dtype is not None else a
 
     def __repr__(self):
-        return 'DeviceArray(shape={}, layout={}, ld={}, c_off={})'.format(self.shape, self.layout, self.ld, self.c_off)
+        return 'DeviceArray(shape={}, layout={}, ld={}, c_off={}, st={})'.format(self.shape, self.layout, self.ld, self.c_off, self.st)
 
 
 class RawInput:

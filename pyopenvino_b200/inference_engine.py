@@ -96,10 +96,16 @@ class IECore:
 
     # OpenVINO Inference Engine API
     def load_network(self, network, device_name: str = 'B200', num_requests: int = 1, batch_size: int = None,
-                     fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True):
+                     fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True, storage: str = 'f32'):
+        """`storage='f16'` (opt-in, SURVEY.md 8(f) NEXT-4): NHWC feature maps between nodes are kept in HBM as FP16 -- half
+        the bytes of every bandwidth-bound layer, and a contraction whose input already is FP16 needs 2 instead of 3
+        tensor-core MMAs per product.  Arithmetic stays FP32 (FP32 accumulate, round to nearest even on store); network
+        inputs, weights, biases, 2-D tensors and results stay FP32.  Results then carry FP16's 2^-11 relative rounding per
+        stored feature map (tolerances: tests/test_gpu_f16_storage.py); the default 'f32' is the reference's precision."""
+        assert storage in ('f32', 'f16')
         if batch_size is not None and batch_size != network.batch_size:
             network.set_batch_size(batch_size)
-        exenet = Executable_Network(network, fuse=fuse, use_graph=use_graph, reuse_buffers=reuse_buffers)
+        exenet = Executable_Network(network, fuse=fuse, use_graph=use_graph, reuse_buffers=reuse_buffers, storage=storage)
         self.check_nodes(exenet.ienet.G)
         exenet.schedule_tasks()
         return exenet
@@ -286,8 +292,10 @@ _OUT_CAPABLE = ('Convolution', 'GroupConvolution', 'MaxPool', 'AvgPool', 'LRN', 
 
 
 class Executable_Network:
-    def __init__(self, ienetwork: IENetwork, fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True):
+    def __init__(self, ienetwork: IENetwork, fuse: bool = True, use_graph: bool = True, reuse_buffers: bool = True,
+                 storage: str = 'f32'):
         self.ienet = ienetwork
+        self.storage = storage
         self.reuse_buffers = reuse_buffers and os.environ.get('B200OV_NO_REUSE') != '1'
         self.expected_result = None     # {node_name: [precision, dims, ndarray]} feature-map ground truth (debug)
         self.kernel_type = 'naive'      # accepted for compatibility: every value runs the CUDA kernels
@@ -520,6 +528,15 @@ class Executable_Network:
         """One pass over the task list.  In planned mode folded nodes are skipped and constants are
         evaluated once (first pass) and kept."""
         from . import kernels
+        prev = kernels.storage
+        kernels.storage = self.storage
+        try:
+            self._run_pass(verbose, capture)
+        finally:
+            kernels.storage = prev
+
+    def _run_pass(self, verbose, capture):
+        from . import kernels
         from .device import is_device
         G = self.ienet.G
         p = self.ienet.ie.plugins
@@ -555,7 +572,11 @@ class Executable_Network:
             fused = {}
             for key, val in step['ops'].items():
                 if key in ('bias', 'scale', 'shift'):
-                    fused[key] = G.nodes[val]['output'][0]['data']
+                    cnode = G.nodes[val]
+                    if 'data' not in cnode['output'][0]:
+                        # eager fused mode: a Parameter scheduled ahead of the Const it folded (`data/mean`) -- evaluate it now
+                        cnode['output'][0]['data'] = p.plugins['Const'].compute(cnode, {}, kernel_type=self.kernel_type, debug=False)[0]
+                    fused[key] = cnode['output'][0]['data']
                 else:
                     fused[key] = val
             if step['out_slot'] is not None:
@@ -637,7 +658,7 @@ class Executable_Network:
             return False
         # what b200ov_conv2d_multi (f16x2 only) accepts -- otherwise the members run one by one and each picks its own
         # kernel (conv_f16x2.cu: f16x2_eligible)
-        if x.ptr % 16 != 0 or x.ld % 4 != 0 or x.shape[1] % 8 != 0:
+        if x.ptr % 16 != 0 or x.ld % (8 if x.st == 'f16' else 4) != 0 or x.shape[1] % 8 != 0:
             return False
         specs, act = [], plan[members[0]]['ops'].get('act')
         for m in members:
@@ -981,14 +1002,16 @@ class Executable_Network:
                 if G.nodes[node]['name'] == node_name:
                     saved_params[node] = G.nodes[node].get('param')
                     G.nodes[node]['param'] = val
-        saved_math = kernels.default_math
+        saved_math, saved_storage = kernels.default_math, self.storage
         kernels.default_math = _cabi.MATH_SAFE
+        self.storage = 'f32'                 # a value beyond FP16 cannot be STORED as FP16 either
         dev.set_arena(None)
         try:
             self._run(verbose=verbose, capture=False)
             self.stream.synchronize()
         finally:
             kernels.default_math = saved_math
+            self.storage = saved_storage
             for node, val in saved_params.items():
                 G.nodes[node]['param'] = val
         return {G.nodes[n]['name']: G.nodes[n]['result'] for n, _ in self.ienet.find_node_by_type('Result')}

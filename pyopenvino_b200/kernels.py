@@ -14,6 +14,33 @@ from .device import DeviceArray
 
 _ACTS = {None: _cabi.ACT_NONE, 'relu': _cabi.ACT_RELU, 'clamp': _cabi.ACT_CLAMP, 'sigmoid': _cabi.ACT_SIGMOID}
 default_math = _cabi.MATH_AUTO
+# Storage type new NHWC feature maps get: 'f32' (the reference's precision, default) or 'f16' (opt-in storage mode, set by
+# the executor for networks loaded with storage='f16').  Arithmetic is FP32 in both; see DeviceArray.st.
+storage = 'f32'
+
+
+def pick_st(c, c_off=0):
+    """Storage type for a new feature map of `c` channels: FP16 needs 8-channel (16-byte) pixel granularity."""
+    return 'f16' if storage == 'f16' and c % 8 == 0 and c_off % 8 == 0 else 'f32'
+
+
+def as_f32(x):
+    """NHWC feature map in float32 storage (a widening copy when it is stored as FP16): the way into kernels that have no
+    FP16-storage variant."""
+    if x.layout != 'nhwc' or x.st == 'f32':
+        return x
+    n, c, h, w = x.shape
+    out = new_nhwc(n, c, h, w, st='f32')
+    _cabi.call('b200ov_copy2d_st', _p(x), x.code, _p(out), out.code, x.pixels, c, x.ld, out.ld, _s())
+    return out
+
+
+def _into(tmp, out):
+    """Result `tmp` computed in a temporary -> the preallocated `out` (other storage type / a Concat slot)."""
+    if out is None or out is tmp:
+        return tmp
+    _cabi.call('b200ov_copy2d_st', _p(tmp), tmp.code, _p(out), out.code, tmp.pixels, tmp.shape[1], tmp.ld, out.ld, _s())
+    return out
 
 
 def _act(act):
@@ -140,9 +167,9 @@ def to_plain(x):
     n, c, h, w = x.shape
     out = DeviceArray(dev.alloc_f32(n * c * h * w), x.shape, 'plain')
     if h * w == 1 and x.is_dense():
-        _cabi.call('b200ov_copy2d', _p(x), _p(out), n, c, x.ld, c, _s())
+        _cabi.call('b200ov_copy2d_st', _p(x), x.code, _p(out), _cabi.DT_F32, n, c, x.ld, c, _s())
     else:
-        _cabi.call('b200ov_transpose', _p(x), _p(out), n, h * w, c, x.ld, h * w, _s())
+        _cabi.call('b200ov_transpose_st', _p(x), x.code, _p(out), _cabi.DT_F32, n, h * w, c, x.ld, h * w, _s())
     return out
 
 
@@ -159,8 +186,10 @@ def as_plain(x):
     return to_plain(x) if x.layout == 'nhwc' else x
 
 
-def new_nhwc(n, c, h, w):
-    return DeviceArray(dev.alloc_f32(n * h * w * c), (n, c, h, w), 'nhwc', ld=c)
+def new_nhwc(n, c, h, w, st=None):
+    st = pick_st(c) if st is None else st
+    elems = n * h * w * c
+    return DeviceArray(dev.alloc_f32(elems if st == 'f32' else (elems + 1) // 2), (n, c, h, w), 'nhwc', ld=c, st=st)
 
 
 def _check_out(out, shape):
@@ -225,6 +254,16 @@ def pack_conv(w):
     return pk
 
 
+def f16x2_ok(x, cin, act_code, mode):
+    """The library's eligibility rule for the f16x2 contraction (conv_f16x2.cu: f16x2_eligible) -- the only kernel that reads
+    or writes FP16-stored feature maps."""
+    if mode not in (_cabi.MATH_AUTO, _cabi.MATH_F16X2) or act_code == _cabi.ACT_SIGMOID or x.ptr % 16 != 0:
+        return False
+    if x.st == 'f16':
+        return x.ld % 8 == 0 and cin % 8 == 0
+    return x.ld % 4 == 0 and (cin % 8 == 0 or (cin <= 4 and x.ld == 4))
+
+
 def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None):
     x = as_nhwc(x)
     pk = w if isinstance(w, PackedWeights) else pack_conv(w)
@@ -232,14 +271,22 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
     assert c == pk.cin, 'input has {} channels, filter expects {}'.format(c, pk.cin)
     oh, ow = out_hw
     shape = (n, pk.cout, oh, ow)
-    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
     code, lo, hi = _act(act)
+    mode = default_math if math is None else math
+    final = _check_out(out, shape) if out is not None else None
+    if not f16x2_ok(x, c, code, mode):
+        x = as_f32(x)                    # the FP32-range kernels read and write float32 feature maps only
+    half_ok = f16x2_ok(x, c, code, mode)
+    if final is not None and (final.st == 'f32' or half_ok):
+        out = final
+    else:
+        out = new_nhwc(*shape, st=pick_st(pk.cout) if half_ok else 'f32')
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=pk.cout, kh=pk.kh, kw=pk.kw, sh=strides[0], sw=strides[1],
                        pt=pads_begin[0], pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, ldw=pk.ldw,
-                       act=code, act_lo=lo, act_hi=hi, math=default_math if math is None else math)
+                       act=code, act_lo=lo, act_hi=hi, math=mode, x_dtype=x.code, y_dtype=out.code)
     b = _vec_ptr(bias, pk.cout)
     _cabi.call('b200ov_conv2d', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(b), _p(out), _s())
-    return out
+    return _into(out, final)
 
 
 def conv1x1_group(x, members, act=None):
@@ -270,19 +317,27 @@ def conv1x1_group(x, members, act=None):
         cache['group_key'] = key
         cache['group'] = (pk, DeviceArray(fb, (total,), 'plain'), col0s, total)
     pk, fb, col0s, total = cache['group']
-    outs = []
+    outs, finals = [], []
+    # one storage type for all members: FP16 only when every member (and every preallocated slot) allows it
+    group_st = 'f16' if all((m[2].st == 'f16') if m[2] is not None else pick_st(w.shape[0]) == 'f16' for w, m in zip(ws, members)) else 'f32'
+    if x.st == 'f16' and not (x.ld % 8 == 0 and x.ptr % 16 == 0):
+        x = as_f32(x)
     segs = (_cabi.ConvSeg * len(members))()
     for i, (w, (_, _b, o)) in enumerate(zip(ws, members)):
         shape = (n, w.shape[0], h, wd)
-        o = _check_out(o, shape) if o is not None else new_nhwc(*shape)
+        final = _check_out(o, shape) if o is not None else None
+        o = final if final is not None and final.st == group_st else new_nhwc(*shape, st=group_st)
+        finals.append(final)
         outs.append(o)
         segs[i].y = o.ptr
         segs[i].col0, segs[i].cout, segs[i].y_ld = col0s[i], w.shape[0], o.ld
     code, lo, hi = _act(act)
+    st = outs[0].st
+    assert all(o.st == st for o in outs), 'grouped convolution outputs must share one storage type'
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=total, kh=1, kw=1, sh=1, sw=1, pt=0, pl=0, oh=h, ow=wd, x_ld=x.ld, y_ld=total,
-                       ldw=pk.ldw, act=code, act_lo=lo, act_hi=hi, math=_cabi.MATH_AUTO)
+                       ldw=pk.ldw, act=code, act_lo=lo, act_hi=hi, math=_cabi.MATH_AUTO, x_dtype=x.code, y_dtype=outs[0].code)
     _cabi.call('b200ov_conv2d_multi', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(fb), len(members), segs, _s())
-    return outs
+    return [_into(o, f) for o, f in zip(outs, finals)]
 
 
 def matmul(a, b, transpose_a=False, transpose_b=True, bias=None, act=None, math=None):
@@ -347,14 +402,23 @@ def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, e
     assert c == g, 'depthwise: {} input channels vs {} groups'.format(c, g)
     oh, ow = out_hw
     shape = (n, c, oh, ow)
-    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
     code, lo, hi = _act(act)
+    final = _check_out(out, shape) if out is not None else None
+    # FP16-stored maps: the TMA tile kernel (3x3, stride 1 / 2, type-preserving); anything else goes through float32
+    half = x.st == 'f16' and not exact and kh == 3 and kw == 3 and strides[0] == strides[1] and strides[0] in (1, 2) and \
+        code <= _cabi.ACT_CLAMP and c % 4 == 0 and x.ld % 8 == 0 and x.ptr % 16 == 0
+    if not half:
+        x = as_f32(x)
+    if final is not None and final.st == x.st and (x.st == 'f32' or (final.ld % 4 == 0 and final.ptr % 8 == 0)):
+        out = final
+    else:
+        out = new_nhwc(*shape, st=x.st)
     d = _cabi.DwConvDesc(n=n, h=h, w=wd, c=c, kh=kh, kw=kw, sh=strides[0], sw=strides[1], pt=pads_begin[0],
                          pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, act=code, act_lo=lo, act_hi=hi,
-                         math=_cabi.DW_EXACT if exact else _cabi.DW_AUTO)
+                         math=_cabi.DW_EXACT if exact else _cabi.DW_AUTO, dtype=x.code)
     b = _vec_ptr(bias, c)
     _cabi.call('b200ov_dwconv2d', C.byref(d), _p(x), C.c_void_p(t.data_ptr()), _p(b), _p(out), _s())
-    return out
+    return _into(out, final)
 
 
 # ---- pooling -----------------------------------------------------------------------------------
@@ -364,12 +428,18 @@ def pool2d(x, mode, kernel, strides, pads_begin, pads_end, out_hw, scale=None, s
     n, c, h, wd = x.shape
     oh, ow = out_hw
     shape = (n, c, oh, ow)
-    out = _check_out(out, shape) if out is not None else new_nhwc(*shape)
+    final = _check_out(out, shape) if out is not None else None
+    if x.st == 'f16' and not (c % 4 == 0 and x.ld % 4 == 0 and x.ptr % 8 == 0):
+        x = as_f32(x)
+    if final is not None and final.st == x.st and (x.st == 'f32' or (final.ld % 4 == 0 and final.ptr % 8 == 0)):
+        out = final
+    else:
+        out = new_nhwc(*shape, st=x.st)                    # pooling keeps the storage type of its input
     d = _cabi.PoolDesc(n=n, h=h, w=wd, c=c, kh=kernel[0], kw=kernel[1], sh=strides[0], sw=strides[1],
                        pt=pads_begin[0], pl=pads_begin[1], pb=pads_end[0], pr=pads_end[1], oh=oh, ow=ow,
-                       x_ld=x.ld, y_ld=out.ld, mode=mode)
+                       x_ld=x.ld, y_ld=out.ld, mode=mode, dtype=x.code)
     _cabi.call('b200ov_pool2d', C.byref(d), _p(x), _p(_vec_ptr(scale, c)), _p(_vec_ptr(shift, c)), _p(out), _s())
-    return out
+    return _into(out, final)
 
 
 # ---- elementwise tail ----------------------------------------------------------------------------
@@ -387,7 +457,7 @@ def _like(x, out=None):
         return _check_out(out, x.shape)
     if x.layout == 'nhwc':
         n, c, h, w = x.shape
-        return new_nhwc(n, c, h, w)
+        return new_nhwc(n, c, h, w, st=x.st)
     return DeviceArray(dev.alloc_f32(x.size), x.shape, 'plain')
 
 
@@ -405,22 +475,25 @@ def _channel_operand_ok(x, b):
 
 def affine_act(x, scale=None, shift=None, act=None, out=None):
     """act(x*scale + shift) with scalar / per-channel operands (either may be None)."""
-    x = as_device(x)
+    x = as_f32(as_device(x))             # standalone elementwise nodes: float32 storage only (fused ones never get here)
     if x.layout == 'plain' and x.ndim == 4 and ((scale is not None and scale.size > 1) or (shift is not None and shift.size > 1)):
         x = to_nhwc(x)
     rows, c, x_ld = _rows_channels(x)
+    final = out
+    if out is not None and out.st != 'f32':
+        out = None
     out = _like(x, out)
     y_ld = out.ld if out.layout == 'nhwc' else c
     sv, ss, hs = _affine_operand(scale, c)
     bv, bs, hb = _affine_operand(shift, c)
     code, lo, hi = _act(act)
     _cabi.call('b200ov_affine_act', _p(x), _p(out), rows, c, x_ld, y_ld, hs, sv, ss, hb, bv, bs, code, lo, hi, _s())
-    return out
+    return _into(out, final) if final is not None and final is not out else out
 
 
 def binary(op, a, b):
     """Same-shape Add (op 0) / Multiply (op 1)."""
-    a, b = as_device(a), as_device(b)
+    a, b = as_f32(as_device(a)), as_f32(as_device(b))
     assert tuple(a.shape) == tuple(b.shape)
     if a.layout != b.layout or not a.is_dense() or not b.is_dense():
         a, b = as_plain(a), as_plain(b)
@@ -440,15 +513,21 @@ def softmax_rows(x):
 
 def lrn(x, size, alpha, beta, bias, out=None):
     x = as_nhwc(x)
+    c = x.shape[1]
+    if x.st == 'f16' and not (c % 4 == 0 and x.ld % 4 == 0 and x.ptr % 8 == 0 and size // 2 <= 4):
+        x = as_f32(x)
+    final = out
+    if out is not None and (out.st != x.st or (x.st == 'f16' and not (out.ld % 4 == 0 and out.ptr % 8 == 0))):
+        out = None
     out = _like(x, out)
-    _cabi.call('b200ov_lrn', _p(x), _p(out), x.pixels, x.shape[1], x.ld, out.ld, size, alpha, beta, bias, _s())
-    return out
+    _cabi.call('b200ov_lrn_st', _p(x), _p(out), x.code, x.pixels, c, x.ld, out.ld, size, alpha, beta, bias, _s())
+    return _into(out, final) if final is not None and final is not out else out
 
 
 def copy_channels(src, dst):
     """Copy an NHWC array into an NHWC channel slice of equal logical shape."""
     assert src.layout == 'nhwc' and dst.layout == 'nhwc' and tuple(src.shape) == tuple(dst.shape)
-    _cabi.call('b200ov_copy2d', _p(src), _p(dst), src.pixels, src.shape[1], src.ld, dst.ld, _s())
+    _cabi.call('b200ov_copy2d_st', _p(src), src.code, _p(dst), dst.code, src.pixels, src.shape[1], src.ld, dst.ld, _s())
     return dst
 
 
@@ -456,7 +535,7 @@ def channel_slice(buf, c_off, c):
     """View of channels [c_off, c_off + c) of an NHWC buffer."""
     n, ct, h, w = buf.shape
     assert buf.layout == 'nhwc' and c_off + c <= ct
-    return DeviceArray(buf.t, (n, c, h, w), 'nhwc', ld=buf.ld, c_off=buf.c_off + c_off)
+    return DeviceArray(buf.t, (n, c, h, w), 'nhwc', ld=buf.ld, c_off=buf.c_off + c_off, st=buf.st)
 
 
 def detection_output(loc, conf, proposals, num_classes, keep_top_k, center_size, variance_in_target, clip_before, clip_after,

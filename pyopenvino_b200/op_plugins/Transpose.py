@@ -36,12 +36,12 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
         y = kernels.as_plain(x)
     elif x.ndim == 4 and perm == [0, 2, 3, 1]:
         if x.layout == 'nhwc':
-            if x.is_dense():
+            if x.is_dense() and x.st == 'f32':
                 y = DeviceArray(x.t, out_shape, 'plain')          # zero-copy: physical layout already is N,H,W,C
-            else:
+            else:                                                 # channel slice, or FP16 storage: one (widening) copy
                 n, c, h, w = x.shape
                 y = DeviceArray(dev.alloc_f32(x.size), out_shape, 'plain')
-                _cabi.call('b200ov_copy2d', C.c_void_p(x.ptr), C.c_void_p(y.ptr), n * h * w, c, x.ld, c,
+                _cabi.call('b200ov_copy2d_st', C.c_void_p(x.ptr), x.code, C.c_void_p(y.ptr), _cabi.DT_F32, n * h * w, c, x.ld, c,
                            C.c_void_p(dev.stream()))
         else:
             n, c, h, w = x.shape

@@ -7,7 +7,7 @@ _lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..
 _lib.b200ov_last_error.restype = C.c_char_p
 
 class PoolDesc(C.Structure):                    # mirrors b200ov_pool_desc in include/b200ov.h
-    _fields_ = [(n, C.c_int32) for n in ('n','h','w','c','kh','kw','sh','sw','pt','pl','pb','pr','oh','ow','x_ld','y_ld','mode')]
+    _fields_ = [(n, C.c_int32) for n in ('n','h','w','c','kh','kw','sh','sw','pt','pl','pb','pr','oh','ow','x_ld','y_ld','mode','dtype')]
 
 def _check(rc):
     if rc != 0:
@@ -33,7 +33,7 @@ def kernel_MaxPool_b200(inputs, strides, pads_begin, pads_end, kernel, rounding_
     _check(_lib.b200ov_malloc(C.byref(dy), C.c_size_t(y.nbytes)))
     _check(_lib.b200ov_memcpy_h2d(dx, x.ctypes.data_as(C.c_void_p), C.c_size_t(x.nbytes), None))
     d = PoolDesc(n, h, w, c, kernel[0], kernel[1], strides[0], strides[1], pads_begin[0], pads_begin[1],
-                 pads_end[0], pads_end[1], oh, ow, c, c, 0)               # mode 0 = B200OV_POOL_MAX
+                 pads_end[0], pads_end[1], oh, ow, c, c, 0, 0)            # mode 0 = B200OV_POOL_MAX, dtype 0 = float32
     _check(_lib.b200ov_pool2d(C.byref(d), dx, None, None, dy, None))
     _check(_lib.b200ov_memcpy_d2h(y.ctypes.data_as(C.c_void_p), dy, C.c_size_t(y.nbytes), None))
     _check(_lib.b200ov_stream_sync(None))
