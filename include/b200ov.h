@@ -65,7 +65,11 @@ enum {
  * default; F16 is the opt-in storage mode (`load_network(..., storage='f16')`): every kernel still computes in FP32 and
  * rounds to nearest even on store, halving the bytes of the bandwidth-bound layers.  The reference's plugins are
  * dtype-generic (common_def.py:18-19) and its original IRs were FP16 (GroupConvolution.py:136-143). */
-enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3 };
+enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3,
+       B200OV_DT_HL = 4   /* network input pre-split for the stem contraction: per pixel (<= 4 channels, 16 bytes)
+                             [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] FP16 pairs with c = hi + 2^-11 lo -- the same
+                             22 significant bits the contraction's own split keeps; only b200ov_conv2d reads it */
+};
 
 /* ---- library / device -------------------------------------------------------------------- */
 int b200ov_version(void);
@@ -240,6 +244,11 @@ int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, i
 int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int hw, int y_ld,
                          int has_scale, const float* scale_vec, float scale_s,
                          int has_shift, const float* shift_vec, float shift_s, void* stream);
+/* The same with the FP16 (hi, lo) split of the f16x2 contraction done here, once per input pixel, instead of once per
+ * filter tap in the stem convolution's producer warps (y: B200OV_DT_HL, pixel pitch 16 bytes; needs C <= 4). */
+int b200ov_input_to_nhwc_split(const void* x, int dtype, void* y, int n, int c, int hw,
+                               int has_scale, const float* scale_vec, float scale_s,
+                               int has_shift, const float* shift_vec, float shift_s, void* stream);
 /* y[i] = (float)x[i]: a non-image (not 4-D) input of element type `dtype` (Parameter.py:13). */
 int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream);
 /* b200ov_transpose / b200ov_copy2d between storage types (F32 / F16): the FP16 storage mode's NHWC feature maps leave

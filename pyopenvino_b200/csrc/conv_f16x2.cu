@@ -109,6 +109,8 @@ struct Params {
   // [ks * num_slots, (ks + 1) * num_slots) of the K range (num_slots = slots per split, even) and writes its raw partial
   // sums to rows [ks * ws_rows + m, ...) of the workspace, which a second kernel reduces in a fixed order.
   int ksplit, ws_rows;
+  int a_hl;                            // 1: x already holds the FP16 (hi, scaled lo) pairs (network input written by the layout
+                                       //    kernel, b200ov_input_to_nhwc_split): the producers only route words, no split
   FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots, d_ksplit;
 };
 
@@ -532,6 +534,15 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           continue;
         }
         uint32_t v[16];
+        if (p.a_hl) {
+          // per pixel (4 channels, 16 bytes): [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)]; a run = two pixels
+          v[0] = __float_as_uint(r0.v[0]); v[1] = __float_as_uint(r0.v[1]); v[8] = __float_as_uint(r0.v[2]); v[9] = __float_as_uint(r0.v[3]);
+          v[4] = __float_as_uint(r0.v[4]); v[5] = __float_as_uint(r0.v[5]); v[12] = __float_as_uint(r0.v[6]); v[13] = __float_as_uint(r0.v[7]);
+          v[2] = __float_as_uint(r1.v[0]); v[3] = __float_as_uint(r1.v[1]); v[10] = __float_as_uint(r1.v[2]); v[11] = __float_as_uint(r1.v[3]);
+          v[6] = __float_as_uint(r1.v[4]); v[7] = __float_as_uint(r1.v[5]); v[14] = __float_as_uint(r1.v[6]); v[15] = __float_as_uint(r1.v[7]);
+          tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
+          continue;
+        }
         split_pair(r0.v[0], r0.v[1], v[0], v[8]);
         split_pair(r0.v[2], r0.v[3], v[1], v[9]);
         split_pair(r1.v[0], r1.v[1], v[2], v[10]);
@@ -650,6 +661,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           uint32_t hw[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            chk = fma2(acc[qb * 16 + j], zero2, chk);              // inf / NaN before the activation hides it (fmaxf drops NaN)
             const float2 u = unpack_f32x2(acc[qb * 16 + j]);
             const float o0 = fminf(fmaxf(u.x, act_lo), act_hi), o1 = fminf(fmaxf(u.y, act_lo), act_hi);
             chk = fma2(mul2(pack_f32x2(o0, o1), big), zero2, chk);
@@ -862,6 +874,9 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
 // pixel pitch of exactly 4 floats (a run = two adjacent taps; the producer of x zero-fills the pad lanes, e.g. the
 // network-input layout kernel writes a 3-channel image with pitch 4).
 bool f16x2_eligible(const b200ov_conv_desc* d, const void* x) {
+  if (d->x_dtype == B200OV_DT_HL)      // pre-split network input: the stem's 8-channel super-pixel view only
+    return d->cin <= 4 && d->x_ld == 4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0 &&
+           d->act != B200OV_ACT_SIGMOID;
   if (d->x_dtype == B200OV_DT_F16)     // FP16 feature map in: 8-channel runs of 16 bytes
     return (d->x_ld % 8 == 0) && aligned16(x) && d->cin % 8 == 0 && d->act != B200OV_ACT_SIGMOID;
   return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || (d->cin <= 4 && d->x_ld == 4)) &&
@@ -977,6 +992,8 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
   // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1.
   { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
+  p.a_hl = d->x_dtype == B200OV_DT_HL ? 1 : 0;
+  if (p.a_hl && p.pair4) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: a pre-split input needs the super-pixel stem path");
   p.wide_loads = !a16 && !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   if (a16) p.prefetch = 0;
   p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);

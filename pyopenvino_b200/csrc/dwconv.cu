@@ -194,8 +194,10 @@ struct DwTmaP {
   uint32_t items;
   FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
 };
-constexpr int DW_TMA_THREADS = 512;
-constexpr int DW_TMA_STAGES = 3;
+constexpr int DW_TMA_CONSUMERS = 512;                       // 16 warps, all consumers; thread 0 also feeds the ring (a 17th warp
+constexpr int DW_TMA_THREADS = DW_TMA_CONSUMERS;            // would cost every thread registers: 5 warps per SM sub-partition)
+constexpr int DW_TMA_STAGES = 4;
+constexpr int DW_TMA_BUDGET = 48 * 1024, DW_TMA_STAGE_CAP = 54 * 1024;
 
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
   f32x2 r;
@@ -212,10 +214,15 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
   extern __shared__ uint8_t dw_smem_raw[];
   const uint32_t base = (smem_u32(dw_smem_raw) + 127u) & ~127u;
   const uint8_t* base_ptr = dw_smem_raw + (base - smem_u32(dw_smem_raw));
-  const uint32_t bars = base + DW_TMA_STAGES * p.stage_bytes;
+  const uint32_t bars = base + DW_TMA_STAGES * p.stage_bytes;            // full[STAGES], empty[STAGES]
+  auto bar_full = [&](uint32_t s) { return bars + 8 * s; };
+  auto bar_empty = [&](uint32_t s) { return bars + 8 * (DW_TMA_STAGES + s); };
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < DW_TMA_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    for (int s = 0; s < DW_TMA_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), DW_TMA_CONSUMERS / 32);
+    }
     fence_mbar_init();
     prefetch_tensormap(&map_x);
   }
@@ -229,15 +236,28 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
     p.d_rowtiles.divmod(q2, c3, q);
     cc = (int)a; ct = (int)b; rt = (int)q; ig = (int)c3;
   };
-  auto issue = [&](uint32_t k) {
+  // Thread 0 feeds the ring: item j may be issued once all 16 warps have drained the stage's previous item (empty
+  // barrier).  Before it waits for item k itself it makes sure k has been issued (blocking on the laggards if it must),
+  // then issues ahead opportunistically (non-blocking probes) so that up to STAGES - 1 tiles are in flight.
+  uint32_t issued = 0;
+  auto issue = [&](uint32_t j) {
     int cc, ct, rt, ig;
-    decode(k, cc, ct, rt, ig);
-    const uint32_t s = k % DW_TMA_STAGES;
-    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.box_bytes);
-    tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
+    decode(j, cc, ct, rt, ig);
+    const uint32_t s = j % DW_TMA_STAGES;
+    mbar_arrive_expect_tx(bar_full(s), (uint32_t)p.box_bytes);
+    tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bar_full(s));
   };
-  if (tid == 0)
-    for (uint32_t k = 0; k < (uint32_t)(DW_TMA_STAGES - 1) && k < my_items; ++k) issue(k);
+  auto feed = [&](uint32_t k) {
+    while (issued < my_items) {
+      const uint32_t s = issued % DW_TMA_STAGES;
+      if (issued >= DW_TMA_STAGES) {
+        const uint32_t par = ((issued / DW_TMA_STAGES) - 1) & 1;
+        if (issued <= k) mbar_wait(bar_empty(s), par);
+        else if (!mbar_test(bar_empty(s), par)) break;
+      }
+      issue(issued++);
+    }
+  };
 
   const int half = tid >> 8, t = tid & 255;
   const int cg = t & 7, lane_col = t >> 3;
@@ -248,9 +268,9 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
   const int r_begin = half * rows_half, r_end = min(p.tr, r_begin + rows_half);
   int cur_c0 = -1;
   ulonglong2 wt[9], bv = make_ulonglong2(0ull, 0ull);
+  constexpr int KEEP = 3 - S;                               // input rows two vertically adjacent windows share
 
   for (uint32_t k = 0; k < my_items; ++k) {
-    if (tid == 0 && k + DW_TMA_STAGES - 1 < my_items) issue(k + DW_TMA_STAGES - 1);
     int cc, ct, rt, ig;
     decode(k, cc, ct, rt, ig);
     const uint32_t s = k % DW_TMA_STAGES;
@@ -264,7 +284,8 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
       for (int tp = 0; tp < 9; ++tp) wt[tp] = __ldg(reinterpret_cast<const ulonglong2*>(wp + tp * p.c + c0));
       bv = bias != nullptr ? __ldg(reinterpret_cast<const ulonglong2*>(bias + c0)) : make_ulonglong2(0ull, 0ull);
     }
-    mbar_wait(bars + 8 * s, (k / DW_TMA_STAGES) & 1);
+    if (tid == 0) feed(k);
+    mbar_wait(bar_full(s), (k / DW_TMA_STAGES) & 1);
     if (active) {
       const T* tile = reinterpret_cast<const T*>(base_ptr + s * p.stage_bytes) +
                       ((size_t)img_l * p.bh * p.bw + (size_t)ox_l * S) * 32 + cg * 4;
@@ -280,35 +301,38 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
           }
         }
       };
-      ulonglong2 R[3][3];
-      constexpr int KEEP = 3 - S;                           // 2 (stride 1) or 1 (stride 2)
-#pragma unroll
+      ulonglong2 R[3][3];                                   // three input rows x three columns, rotating BY NAME:
+#pragma unroll                                              // the loop below is unrolled over one rotation period
       for (int i = 0; i < KEEP; ++i) load_row(r_begin * S + i, R[i]);
       const int oy0 = rt * p.tr;
       T* yp = y + (((size_t)img * p.oh + oy0 + r_begin) * p.ow + ox) * p.y_ld + c0;
       const size_t yrow = (size_t)p.ow * p.y_ld;
-      for (int r = r_begin; r < r_end && oy0 + r < p.oh; ++r) {
+      const int r_stop = min(r_end, p.oh - oy0);
+      for (int r = r_begin; r < r_stop; r += 3) {
 #pragma unroll
-        for (int i = KEEP; i < 3; ++i) load_row(r * S + i, R[i]);
-        f32x2 lo = bv.x, hi = bv.y;
+        for (int ph = 0; ph < 3; ++ph) {
+          if (r + ph < r_stop) {
+            const int b0 = (ph * S) % 3;                    // compile-time after unrolling: window row ky lives in R[(b0 + ky) % 3]
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+            for (int i = KEEP; i < 3; ++i) load_row((r + ph) * S + i, R[(b0 + i) % 3]);
+            f32x2 lo = bv.x, hi = bv.y;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            lo = fma2(R[ky][kx].x, wt[ky * 3 + kx].x, lo);
-            hi = fma2(R[ky][kx].y, wt[ky * 3 + kx].y, hi);
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                lo = fma2(R[(b0 + ky) % 3][kx].x, wt[ky * 3 + kx].x, lo);
+                hi = fma2(R[(b0 + ky) % 3][kx].y, wt[ky * 3 + kx].y, hi);
+              }
+            const float2 a = unpack2(lo), b = unpack2(hi);
+            IO::st(yp, make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
+                                   act_t<ACT>(b.y, p.lo, p.hi)));
+            yp += yrow;
           }
-        const float2 a = unpack2(lo), b = unpack2(hi);
-        IO::st(yp, make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
-                               act_t<ACT>(b.y, p.lo, p.hi)));
-        yp += yrow;
-#pragma unroll
-        for (int i = 0; i < KEEP; ++i)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) R[i][kx] = R[i + S][kx];
+        }
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(bar_empty(s));         // this warp is done with stage s
   }
 }
 
@@ -321,7 +345,7 @@ static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q, int esize) {
   if (q.nimg > d->n) q.nimg = d->n;
   if (q.nimg < 1) q.nimg = 1;
   q.bw = (q.tw - 1) * S + K;
-  const int budget = 64 * 1024;
+  const int budget = DW_TMA_BUDGET;
   int tr = d->oh;
   while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
   if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {
@@ -334,7 +358,7 @@ static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q, int esize) {
   q.bh = (q.tr - 1) * S + K;
   q.box_bytes = q.nimg * q.bh * q.bw * cb;
   q.stage_bytes = round_up(q.box_bytes, 128);
-  if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
+  if (q.stage_bytes > DW_TMA_STAGE_CAP || q.bw > 256 || q.bh > 256) return false;
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
   const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
   if (items <= 0 || items > 0x7fffffffLL) return false;
@@ -350,10 +374,10 @@ static int launch_dw_tma(const DwTmaP& q, const CUtensorMap& map, const float* w
   auto kern = dwconv3x3_tma_kernel<S, ACT, T>;
   static bool configured = false;
   if (!configured) {
-    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * 72 * 1024 + 8 * DW_TMA_STAGES + 256));
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * DW_TMA_STAGE_CAP + 16 * DW_TMA_STAGES + 256));
     configured = true;
   }
-  const int need = DW_TMA_STAGES * q.stage_bytes + 8 * DW_TMA_STAGES + 256;
+  const int need = DW_TMA_STAGES * q.stage_bytes + 16 * DW_TMA_STAGES + 256;
   const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
   kern<<<grid, DW_TMA_THREADS, need, s>>>(q, map, wp, bias, y);
   B200OV_LAUNCH_CHECK("dwconv3x3_tma_kernel");

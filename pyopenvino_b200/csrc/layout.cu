@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "f16split.cuh"
 
 namespace b200ov {
 
@@ -89,7 +90,18 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TIN* __r
         if (has_shift) v[ch] = __fadd_rn(v[ch], sf[ch]);
       }
     }
-    if constexpr (PAD == 4) {
+    if constexpr (PAD == 44) {
+      // pre-split for the stem contraction: [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)], 16 bytes per pixel like 4 floats
+      __half h[4], l[4];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) split_f16x2(v[ch], h[ch], l[ch]);
+      const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+      const __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+      uint4 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h01); o.y = *reinterpret_cast<const uint32_t*>(&h23);
+      o.z = *reinterpret_cast<const uint32_t*>(&l01); o.w = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint4*>(y + pix * 4) = o;
+    } else if constexpr (PAD == 4) {
       *reinterpret_cast<float4*>(y + pix * 4) = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (PAD == 8) {
       *reinterpret_cast<float4*>(y + pix * 8) = make_float4(v[0], v[1], v[2], v[3]);
@@ -235,6 +247,16 @@ static int input_to_nhwc_typed(const TIN* x, float* y, int n, int c, int hw, int
   return B200OV_OK;
 }
 
+template <typename TIN>
+static int input_to_nhwc_split_typed(const TIN* x, float* y, int n, int c, int hw, int has_scale, const float* scale_vec, float scale_s,
+                                     int has_shift, const float* shift_vec, float shift_s, cudaStream_t s) {
+  const long long pixels = (long long)n * hw;
+  nchw_to_nhwc_smallc_kernel<4, 44, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, 4, has_scale, scale_vec, scale_s,
+                                                                            has_shift, shift_vec, shift_s);
+  B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
+  return B200OV_OK;
+}
+
 // plain (non 4-D) inputs: widen only
 template <typename TIN>
 __global__ void __launch_bounds__(256) widen_kernel(const TIN* __restrict__ x, float* __restrict__ y, long long count) {
@@ -258,6 +280,21 @@ int b200ov_nchw_to_nhwc_affine(const float* x, float* y, int n, int c, int hw, i
                                float shift_s, void* stream) {
   return b200ov_input_to_nhwc(x, B200OV_DT_F32, y, n, c, hw, y_ld, has_scale, scale_vec, scale_s, has_shift, shift_vec,
                               shift_s, stream);
+}
+
+int b200ov_input_to_nhwc_split(const void* x, int dtype, void* y, int n, int c, int hw, int has_scale, const float* scale_vec,
+                               float scale_s, int has_shift, const float* shift_vec, float shift_s, void* stream) {
+  B200OV_REQUIRE(x && y && n >= 0 && c > 0 && c <= 4 && hw > 0 && aligned16(y), "input_to_nhwc_split: bad argument (needs C <= 4)");
+  if (n == 0) return B200OV_OK;
+  float* yf = static_cast<float*>(y);
+  cudaStream_t s = as_stream(stream);
+  switch (dtype) {
+    case B200OV_DT_F32: return input_to_nhwc_split_typed(static_cast<const float*>(x), yf, n, c, hw, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s, s);
+    case B200OV_DT_F16: return input_to_nhwc_split_typed(static_cast<const __half*>(x), yf, n, c, hw, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s, s);
+    case B200OV_DT_U8: return input_to_nhwc_split_typed(static_cast<const uint8_t*>(x), yf, n, c, hw, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s, s);
+    case B200OV_DT_I8: return input_to_nhwc_split_typed(static_cast<const int8_t*>(x), yf, n, c, hw, has_scale, scale_vec, scale_s, has_shift, shift_vec, shift_s, s);
+    default: return set_error(B200OV_ERR_INVALID, "input_to_nhwc_split: unknown element type %d", dtype);
+  }
 }
 
 int b200ov_input_to_nhwc(const void* x, int dtype, float* y, int n, int c, int hw, int y_ld, int has_scale,

@@ -157,8 +157,10 @@ struct PoolTmaP {
   FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
 };
 
-constexpr int POOL_TMA_THREADS = 512;
-constexpr int POOL_TMA_STAGES = 3;
+constexpr int POOL_TMA_CONSUMERS = 512;                     // 16 consumer warps
+constexpr int POOL_TMA_THREADS = POOL_TMA_CONSUMERS + 32;   // + the TMA producer warp
+constexpr int POOL_TMA_STAGES = 4;
+constexpr int POOL_TMA_BUDGET = 48 * 1024, POOL_TMA_STAGE_CAP = 54 * 1024;     // bytes per stage: target / hard limit (4 stages < 227 KB)
 
 template <int K, int S, typename T>
 __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const PoolTmaP p, const __grid_constant__ CUtensorMap map_x,
@@ -169,10 +171,15 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
   extern __shared__ uint8_t pool_smem_raw[];
   const uint32_t base = (smem_u32(pool_smem_raw) + 127u) & ~127u;
   const uint8_t* base_ptr = pool_smem_raw + (base - smem_u32(pool_smem_raw));
-  const uint32_t bars = base + POOL_TMA_STAGES * p.stage_bytes;          // full[STAGES]
+  const uint32_t bars = base + POOL_TMA_STAGES * p.stage_bytes;          // full[STAGES], empty[STAGES]
+  auto bar_full = [&](uint32_t s) { return bars + 8 * s; };
+  auto bar_empty = [&](uint32_t s) { return bars + 8 * (POOL_TMA_STAGES + s); };
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < POOL_TMA_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    for (int s = 0; s < POOL_TMA_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), POOL_TMA_CONSUMERS / 32);
+    }
     fence_mbar_init();
     prefetch_tensormap(&map_x);
   }
@@ -186,15 +193,20 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
     p.d_rowtiles.divmod(q2, c3, q);
     cc = (int)a; ct = (int)b; rt = (int)q; ig = (int)c3;
   };
-  auto issue = [&](uint32_t k) {
-    int cc, ct, rt, ig;
-    decode(k, cc, ct, rt, ig);
-    const uint32_t s = k % POOL_TMA_STAGES;
-    mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)p.box_bytes);
-    tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bars + 8 * s);
-  };
-  if (tid == 0)
-    for (uint32_t k = 0; k < (uint32_t)(POOL_TMA_STAGES - 1) && k < my_items; ++k) issue(k);
+  if (tid >= POOL_TMA_CONSUMERS) {
+    // ---- producer warp: one lane keeps the ring full; it only ever waits for a stage to be drained by all 16 consumer warps
+    if (tid == POOL_TMA_CONSUMERS) {
+      for (uint32_t k = 0; k < my_items; ++k) {
+        const uint32_t s = k % POOL_TMA_STAGES;
+        if (k >= POOL_TMA_STAGES) mbar_wait(bar_empty(s), ((k / POOL_TMA_STAGES) - 1) & 1);
+        int cc, ct, rt, ig;
+        decode(k, cc, ct, rt, ig);
+        mbar_arrive_expect_tx(bar_full(s), (uint32_t)p.box_bytes);
+        tma::load_4d(base + s * p.stage_bytes, &map_x, cc * 32, ct * p.tw * S - p.pl, rt * p.tr * S - p.pt, ig * p.nimg, bar_full(s));
+      }
+    }
+    return;
+  }
 
   // fixed per-thread geometry
   const int half = tid >> 8, t = tid & 255;
@@ -208,11 +220,10 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 
   for (uint32_t k = 0; k < my_items; ++k) {
-    if (tid == 0 && k + POOL_TMA_STAGES - 1 < my_items) issue(k + POOL_TMA_STAGES - 1);     // its stage was drained in iteration k - 1
     int cc, ct, rt, ig;
     decode(k, cc, ct, rt, ig);
     const uint32_t s = k % POOL_TMA_STAGES;
-    mbar_wait(bars + 8 * s, (k / POOL_TMA_STAGES) & 1);
+    mbar_wait(bar_full(s), (k / POOL_TMA_STAGES) & 1);
     const int c0 = cc * 32 + cg * 4;
     const int img = ig * p.nimg + (int)img_l;
     const int ox = ct * p.tw + (int)ox_l;
@@ -265,7 +276,8 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
         yp += yrow;
       }
     }
-    __syncthreads();                                      // stage s is free again
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(bar_empty(s));       // this warp is done with stage s
   }
 }
 
@@ -280,7 +292,7 @@ static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q, int esize) {
   if (q.nimg > d->n) q.nimg = d->n;
   if (q.nimg < 1) q.nimg = 1;
   q.bw = (q.tw - 1) * S + K;
-  const int budget = 64 * 1024;
+  const int budget = POOL_TMA_BUDGET;
   int tr = d->oh;
   while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
   if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {       // several images do not fit even one row
@@ -293,7 +305,7 @@ static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q, int esize) {
   q.bh = (q.tr - 1) * S + K;
   q.box_bytes = q.nimg * q.bh * q.bw * cb;
   q.stage_bytes = round_up(q.box_bytes, 128);
-  if (q.stage_bytes > 72 * 1024 || q.bw > 256 || q.bh > 256) return false;
+  if (q.stage_bytes > POOL_TMA_STAGE_CAP || q.bw > 256 || q.bh > 256) return false;
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
   const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
   if (items <= 0 || items > 0x7fffffffLL) return false;
@@ -308,12 +320,12 @@ template <int K, int S, typename T>
 static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const float* scale, const float* shift, T* y, cudaStream_t s) {
   auto kern = pool_max_tma_kernel<K, S, T>;
   static bool configured = false;
-  const int smem = POOL_TMA_STAGES * 72 * 1024 + 8 * POOL_TMA_STAGES + 256;
+  const int smem = POOL_TMA_STAGES * POOL_TMA_STAGE_CAP + 16 * POOL_TMA_STAGES + 256;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int need = POOL_TMA_STAGES * q.stage_bytes + 8 * POOL_TMA_STAGES + 256;
+  const int need = POOL_TMA_STAGES * q.stage_bytes + 16 * POOL_TMA_STAGES + 256;
   const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
   kern<<<grid, POOL_TMA_THREADS, need, s>>>(q, map, scale, shift, y);
   B200OV_LAUNCH_CHECK("pool_max_tma_kernel");

@@ -244,6 +244,8 @@ class DeviceArray:
                     [c_off, c_off + C) of each pixel.
     `st` is the STORAGE type of an 'nhwc' feature map: 'f32' (default, the reference's precision) or 'f16' (opt-in
     storage mode, `load_network(..., storage='f16')`: half the bytes, every kernel still computes in FP32).  The logical
+    'hl' marks a network input the layout kernel already split into the contraction's FP16 (hi, lo) pairs (same 4 bytes
+    per value; only the stem Convolution reads it).  The logical
     `dtype` the plugin contract validates stays float32 either way; `t` is always a float32 torch tensor used as raw
     storage (an 'f16' map of n elements occupies ceil(n / 2) of its floats).
     """
@@ -266,7 +268,7 @@ class DeviceArray:
 
     @property
     def code(self):
-        return _cabi.DT_F16 if self.st == 'f16' else _cabi.DT_F32
+        return {'f32': _cabi.DT_F32, 'f16': _cabi.DT_F16, 'hl': _cabi.DT_HL}[self.st]
 
     @property
     def ptr(self):

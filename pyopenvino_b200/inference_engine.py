@@ -457,6 +457,16 @@ class Executable_Network:
                         ops['shift'] = c
                         absorb(n, nxt)
                         tail = nxt
+                # The stem: when the only consumer is a Convolution that runs on the 8-channel super-pixel view of a
+                # <= 4-channel image (even width, even horizontal stride), the layout kernel writes the contraction's
+                # FP16 (hi, lo) pairs directly -- the split then costs once per pixel instead of once per filter tap in
+                # the stem's producer warps (its limiter: 650 cycles per slot against 343 of MMA time, round 1).
+                nxt = self._single_consumer(tail)
+                if nxt is not None and G.nodes[nxt]['type'] == 'Convolution' and channels <= 4 and os.environ.get('B200OV_NO_SPLIT_INPUT') != '1':
+                    cd = G.nodes[nxt]['data']
+                    if G.edges[(tail, nxt)]['connection'][3] == 0 and common_def.string_to_tuple(cd['strides'])[1] % 2 == 0 and \
+                            out_dims[3] % 2 == 0 and common_def.string_to_tuple(cd['dilations']) == (1, 1):
+                        ops['split'] = True
         # Concat in place: producers whose only consumer is a channel Concat write into its buffer
         for n in self.task_list:
             node = G.nodes[n]

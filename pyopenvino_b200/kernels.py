@@ -134,15 +134,20 @@ def to_nhwc(x, scale=None, shift=None, out=None):
     return out
 
 
-def input_to_device(raw, scale=None, shift=None, nhwc=True):
+def input_to_device(raw, scale=None, shift=None, nhwc=True, split=False):
     """RawInput (native element type, IR layout) -> float32 DeviceArray: NHWC (+ folded scale / shift) for 4-D inputs
     when `nhwc`, else a plain widened copy.  One kernel; the widening is exact."""
     if raw.ndim == 4 and nhwc:
         n, c, h, w = raw.shape
         ld = 4 if c == 3 else c
-        out = DeviceArray(dev.alloc_f32(n * h * w * ld), raw.shape, 'nhwc', ld=ld)
         sv, ss, hs = _affine_operand(scale, c)
         bv, bs, hb = _affine_operand(shift, c)
+        if split and c <= 4:
+            # the stem Convolution is the only consumer: write the FP16 (hi, lo) pairs of the contraction here, once per pixel
+            out = DeviceArray(dev.alloc_f32(n * h * w * 4), raw.shape, 'nhwc', ld=4, st='hl')
+            _cabi.call('b200ov_input_to_nhwc_split', C.c_void_p(raw.ptr), raw.code, _p(out), n, c, h * w, hs, sv, ss, hb, bv, bs, _s())
+            return out
+        out = DeviceArray(dev.alloc_f32(n * h * w * ld), raw.shape, 'nhwc', ld=ld)
         _cabi.call('b200ov_input_to_nhwc', C.c_void_p(raw.ptr), raw.code, _p(out), n, c, h * w, out.ld, hs, sv, ss, hb, bv, bs, _s())
         return out
     assert scale is None and shift is None
@@ -261,6 +266,8 @@ def f16x2_ok(x, cin, act_code, mode):
         return False
     if x.st == 'f16':
         return x.ld % 8 == 0 and cin % 8 == 0
+    if x.st == 'hl':
+        return True                      # produced for exactly this consumer (inference_engine.build_plan checks the geometry)
     return x.ld % 4 == 0 and (cin % 8 == 0 or (cin <= 4 and x.ld == 4))
 
 
@@ -274,6 +281,8 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
     code, lo, hi = _act(act)
     mode = default_math if math is None else math
     final = _check_out(out, shape) if out is not None else None
+    if x.st == 'hl' and mode not in (_cabi.MATH_AUTO, _cabi.MATH_F16X2):
+        raise _cabi.B200ovError('a pre-split network input can only feed the f16x2 contraction')
     if not f16x2_ok(x, c, code, mode):
         x = as_f32(x)                    # the FP32-range kernels read and write float32 feature maps only
     half_ok = f16x2_ok(x, c, code, mode)

@@ -7,7 +7,7 @@ conversion kernel through `fused`.
 """
 import numpy as np
 
-from .. import common_def, kernels
+from .. import _cabi, common_def, kernels
 from ..device import DeviceArray, RawInput, is_device, native_input
 
 
@@ -33,7 +33,9 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
         assert tuple(raw.shape) == tuple(shape)
         if raw.np_dtype == np.float32 and not (raw.ndim == 4 and to_nhwc):
             return {0: DeviceArray(raw.t, raw.shape, 'plain')}
-        return {0: kernels.input_to_device(raw, scale=f.get('scale'), shift=f.get('shift'), nhwc=bool(to_nhwc))}
+        return {0: kernels.input_to_device(raw, scale=f.get('scale'), shift=f.get('shift'), nhwc=bool(to_nhwc),
+                                           split=bool(f.get('split')) and kernels.default_math == _cabi.MATH_AUTO and
+                                           kernel_type not in ('fp32', 'tf32x3', 'tf32', 'safe'))}
     else:
         x = kernels.upload(np.array(param).reshape(shape).astype(precision))
     if x.ndim == 4 and to_nhwc:
