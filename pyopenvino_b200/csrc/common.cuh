@@ -60,6 +60,39 @@ __device__ __forceinline__ float apply_act(float v, int act, float lo, float hi)
   }
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Every kernel of the per-inference launch sequence is launched with programmatic stream serialization: its CTAs may be
+// scheduled (and run their prologue: barrier init, TMEM allocation, tensor-map prefetch, weight loads) while the previous
+// kernel of the stream is still draining, instead of after launch latency + a full drain.  The contract each kernel keeps:
+//   * B200OV_PDL_SYNC() before its first read of a tensor another kernel produced AND before its first global write
+//     (per-inference buffers are recycled, so the previous kernel may still be reading what this one overwrites);
+//     constants (weights, biases, descriptors) may be read before it;
+//   * the trigger comes after the wait, so at most one dependent grid is ever launched ahead (no chains of waiting grids).
+// `griddepcontrol.wait` returns at once when the kernel was launched without the attribute.  B200OV_PDL=0 disables it.
+#define B200OV_PDL_SYNC()                                            \
+  do {                                                               \
+    asm volatile("griddepcontrol.wait;" ::: "memory");               \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Grid size for grid-stride bandwidth kernels: enough CTAs to fill every SM a few times over,

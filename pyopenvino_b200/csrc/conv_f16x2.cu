@@ -827,7 +827,7 @@ static int launch(const Params& p, const void* x, const float* bias, unsigned in
     configured = true;
   }
   const int grid = p.num_tiles < props().sm_count ? p.num_tiles : props().sm_count;
-  kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(p, x, bias, status, mh, ml, my[0], my[1], my[2]);
+  launch_k(kern, grid, NUM_THREADS, L::TOTAL, s, p, x, bias, status, mh, ml, my[0], my[1], my[2]);
   B200OV_LAUNCH_CHECK("conv_f16x2_kernel");
   return B200OV_OK;
 }
@@ -1077,10 +1077,10 @@ int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const void* x, const float* w
   if (rc) return rc;
   const bool vec = d->cout % 4 == 0 && d->y_ld % 4 == 0 && aligned16(y) && (bias == nullptr || aligned16(bias));
   if (vec)
-    splitk_reduce_kernel<4><<<bw_grid(M * (d->cout / 4), 256), 256, 0, s>>>(ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit,
+    launch_k(splitk_reduce_kernel<4>, bw_grid(M * (d->cout / 4), 256), 256, 0, s, ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit,
                                                                          d->act, d->act_lo, d->act_hi);
   else
-    splitk_reduce_kernel<1><<<bw_grid(M * d->cout, 256), 256, 0, s>>>(ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit, d->act,
+    launch_k(splitk_reduce_kernel<1>, bw_grid(M * d->cout, 256), 256, 0, s, ws, bias, y, (int)M, d->cout, ws_rows, ws_ld, d->y_ld, ksplit, d->act,
                                                                    d->act_lo, d->act_hi);
   B200OV_LAUNCH_CHECK("splitk_reduce_kernel");
   return B200OV_OK;

@@ -226,9 +226,9 @@ static int launch_cfg(const ConvP& p0, bool vec, const float* x, const float* wp
   long long blocks = (long long)ceil_div(p.M, BM) * p.nb_n;
   if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d grid too large");
   if (vec)
-    conv_ffma_kernel<BM, BN, TM, TN, true><<<(unsigned)blocks, NT, 0, s>>>(p, x, wp, bias, y);
+    launch_k(conv_ffma_kernel<BM, BN, TM, TN, true>, (unsigned)blocks, NT, 0, s, p, x, wp, bias, y);
   else
-    conv_ffma_kernel<BM, BN, TM, TN, false><<<(unsigned)blocks, NT, 0, s>>>(p, x, wp, bias, y);
+    launch_k(conv_ffma_kernel<BM, BN, TM, TN, false>, (unsigned)blocks, NT, 0, s, p, x, wp, bias, y);
   B200OV_LAUNCH_CHECK("conv_ffma_kernel");
   return B200OV_OK;
 }

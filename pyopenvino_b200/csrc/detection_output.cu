@@ -179,7 +179,7 @@ extern "C" int b200ov_detection_output(const b200ov_detection_desc* d, const flo
     B200OV_CUDA(cudaFuncSetAttribute(detection_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  detection_output_kernel<<<d->n, 1024, smem, as_stream(stream)>>>(p, loc, conf, proposals, out);
+  launch_k(detection_output_kernel, d->n, 1024, smem, as_stream(stream), p, loc, conf, proposals, out);
   B200OV_LAUNCH_CHECK("detection_output_kernel");
   return B200OV_OK;
 }

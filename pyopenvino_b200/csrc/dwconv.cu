@@ -197,7 +197,7 @@ struct DwTmaP {
 constexpr int DW_TMA_CONSUMERS = 512;                       // 16 warps, all consumers; thread 0 also feeds the ring (a 17th warp
 constexpr int DW_TMA_THREADS = DW_TMA_CONSUMERS;            // would cost every thread registers: 5 warps per SM sub-partition)
 constexpr int DW_TMA_STAGES = 4;
-constexpr int DW_TMA_BUDGET = 48 * 1024, DW_TMA_STAGE_CAP = 54 * 1024;
+constexpr int DW_TMA_STAGE_BYTES = 56 * 1024;       // per stage; 4 stages + barriers < 227 KB
 
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
   f32x2 r;
@@ -337,35 +337,18 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
 }
 
 static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q, int esize) {
-  const int K = 3, S = d->sh;
-  const int cb = 32 * esize;
-  const int col_tiles = ceil_div(d->ow, 32);
-  q.tw = ceil_div(d->ow, col_tiles);
-  q.nimg = 32 / q.tw;
-  if (q.nimg > d->n) q.nimg = d->n;
-  if (q.nimg < 1) q.nimg = 1;
-  q.bw = (q.tw - 1) * S + K;
-  const int budget = DW_TMA_BUDGET;
-  int tr = d->oh;
-  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
-  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {
-    q.nimg = 1;
-    tr = d->oh;
-    while (tr > 1 && ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
-  }
-  const int row_tiles = ceil_div(d->oh, tr);
-  q.tr = ceil_div(d->oh, row_tiles);
-  q.bh = (q.tr - 1) * S + K;
-  q.box_bytes = q.nimg * q.bh * q.bw * cb;
-  q.stage_bytes = round_up(q.box_bytes, 128);
-  if (q.stage_bytes > DW_TMA_STAGE_CAP || q.bw > 256 || q.bh > 256) return false;
+  tma::TilePlan t;
+  if (!tma::plan_tiles(d->n, d->oh, d->ow, 3, d->sh, 32 * esize, DW_TMA_STAGE_BYTES, t)) return false;
+  q.tw = t.tw; q.tr = t.tr; q.nimg = t.nimg; q.bw = t.bw; q.bh = t.bh;
+  q.box_bytes = t.box_bytes;
+  q.stage_bytes = round_up(t.box_bytes, 128);
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
-  const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
+  const long long items = (long long)img_groups * t.row_tiles * t.col_tiles * cchunks;
   if (items <= 0 || items > 0x7fffffffLL) return false;
   q.items = (uint32_t)items;
   q.n = d->n; q.c = d->c; q.oh = d->oh; q.ow = d->ow; q.y_ld = d->y_ld; q.pt = d->pt; q.pl = d->pl;
   q.lo = d->act_lo; q.hi = d->act_hi;
-  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(col_tiles); q.d_rowtiles = FastDiv(row_tiles); q.d_tw = FastDiv(q.tw);
+  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(t.col_tiles); q.d_rowtiles = FastDiv(t.row_tiles); q.d_tw = FastDiv(q.tw);
   return true;
 }
 
@@ -374,12 +357,12 @@ static int launch_dw_tma(const DwTmaP& q, const CUtensorMap& map, const float* w
   auto kern = dwconv3x3_tma_kernel<S, ACT, T>;
   static bool configured = false;
   if (!configured) {
-    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * DW_TMA_STAGE_CAP + 16 * DW_TMA_STAGES + 256));
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_TMA_STAGES * DW_TMA_STAGE_BYTES + 16 * DW_TMA_STAGES + 256));
     configured = true;
   }
   const int need = DW_TMA_STAGES * q.stage_bytes + 16 * DW_TMA_STAGES + 256;
   const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
-  kern<<<grid, DW_TMA_THREADS, need, s>>>(q, map, wp, bias, y);
+  launch_k(kern, grid, DW_TMA_THREADS, need, s, q, map, wp, bias, y);
   B200OV_LAUNCH_CHECK("dwconv3x3_tma_kernel");
   return B200OV_OK;
 }

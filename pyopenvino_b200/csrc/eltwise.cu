@@ -188,17 +188,17 @@ int b200ov_affine_act(const float* x, float* y, int64_t rows, int c, int x_ld, i
   if (scale_vec == nullptr && shift_vec == nullptr && x_ld == c && y_ld == c && (rows * c) % 4 == 0 && rows * c < 0x7fffffffLL &&
       aligned16(x) && aligned16(y) && c % 4 != 0) {
     const int flat = (int)(rows * c);
-    affine_act_kernel<4><<<bw_grid(flat / 4, 256), 256, 0, s>>>(x, y, 1, flat, flat, flat, has_scale, nullptr, scale_s, has_shift,
+    launch_k(affine_act_kernel<4>, bw_grid(flat / 4, 256), 256, 0, s, x, y, 1, flat, flat, flat, has_scale, nullptr, scale_s, has_shift,
                                                              nullptr, shift_s, act, act_lo, act_hi);
     B200OV_LAUNCH_CHECK("affine_act_kernel");
     return B200OV_OK;
   }
   const bool vec = (c % 4 == 0) && (x_ld % 4 == 0) && (y_ld % 4 == 0) && aligned16(x) && aligned16(y);
   if (vec)
-    affine_act_kernel<4><<<bw_grid(rows * (c / 4), 256), 256, 0, s>>>(x, y, rows, c, x_ld, y_ld, has_scale, scale_vec, scale_s,
+    launch_k(affine_act_kernel<4>, bw_grid(rows * (c / 4), 256), 256, 0, s, x, y, rows, c, x_ld, y_ld, has_scale, scale_vec, scale_s,
                                                                       has_shift, shift_vec, shift_s, act, act_lo, act_hi);
   else
-    affine_act_kernel<1><<<bw_grid(rows * c, 256), 256, 0, s>>>(x, y, rows, c, x_ld, y_ld, has_scale, scale_vec, scale_s,
+    launch_k(affine_act_kernel<1>, bw_grid(rows * c, 256), 256, 0, s, x, y, rows, c, x_ld, y_ld, has_scale, scale_vec, scale_s,
                                                                 has_shift, shift_vec, shift_s, act, act_lo, act_hi);
   B200OV_LAUNCH_CHECK("affine_act_kernel");
   return B200OV_OK;
@@ -209,9 +209,9 @@ int b200ov_binary(int op, const float* a, const float* b, float* y, int64_t coun
   if (count == 0) return B200OV_OK;
   cudaStream_t s = as_stream(stream);
   if (count % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(y))
-    binary_kernel<4><<<bw_grid(count / 4, 256), 256, 0, s>>>(op, a, b, y, count);
+    launch_k(binary_kernel<4>, bw_grid(count / 4, 256), 256, 0, s, op, a, b, y, count);
   else
-    binary_kernel<1><<<bw_grid(count, 256), 256, 0, s>>>(op, a, b, y, count);
+    launch_k(binary_kernel<1>, bw_grid(count, 256), 256, 0, s, op, a, b, y, count);
   B200OV_LAUNCH_CHECK("binary_kernel");
   return B200OV_OK;
 }
@@ -219,7 +219,7 @@ int b200ov_binary(int op, const float* a, const float* b, float* y, int64_t coun
 int b200ov_softmax(const float* x, float* y, int rows, int cols, void* stream) {
   B200OV_REQUIRE(x && y && rows >= 0 && cols > 0, "softmax: bad argument");
   if (rows == 0) return B200OV_OK;
-  softmax_kernel<<<rows, 128, 0, as_stream(stream)>>>(x, y, cols);
+  launch_k(softmax_kernel, rows, 128, 0, as_stream(stream), x, y, cols);
   B200OV_LAUNCH_CHECK("softmax_kernel");
   return B200OV_OK;
 }
@@ -239,9 +239,9 @@ int b200ov_lrn_st(const void* x, void* y, int dtype, int64_t pixels, int c, int 
   const __half* xh = static_cast<const __half*>(x);
   __half* yh = static_cast<__half*>(y);
   if (size / 2 == 2)
-    lrn_vec4_kernel<2, __half><<<g, 256, 0, as_stream(stream)>>>(xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, 2, alpha, beta, bias);
+    launch_k(lrn_vec4_kernel<2, __half>, g, 256, 0, as_stream(stream), xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, 2, alpha, beta, bias);
   else
-    lrn_vec4_kernel<0, __half><<<g, 256, 0, as_stream(stream)>>>(xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, size / 2, alpha, beta, bias);
+    launch_k(lrn_vec4_kernel<0, __half>, g, 256, 0, as_stream(stream), xh, yh, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, size / 2, alpha, beta, bias);
   B200OV_LAUNCH_CHECK("lrn_kernel");
   return B200OV_OK;
 }
@@ -256,11 +256,11 @@ int b200ov_lrn(const float* x, float* y, int64_t pixels, int c, int x_ld, int y_
   if (vec) {
     const int g = bw_grid(items, 256);
     if (size / 2 == 2)
-      lrn_vec4_kernel<2><<<g, 256, 0, as_stream(stream)>>>(x, y, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, 2, alpha, beta, bias);
+      launch_k(lrn_vec4_kernel<2>, g, 256, 0, as_stream(stream), x, y, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, 2, alpha, beta, bias);
     else
-      lrn_vec4_kernel<0><<<g, 256, 0, as_stream(stream)>>>(x, y, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, size / 2, alpha, beta, bias);
+      launch_k(lrn_vec4_kernel<0>, g, 256, 0, as_stream(stream), x, y, (uint32_t)items, FastDiv(c / 4), x_ld, y_ld, size / 2, alpha, beta, bias);
   } else {
-    lrn_kernel<<<bw_grid(pixels * c, 256), 256, 0, as_stream(stream)>>>(x, y, pixels, c, x_ld, y_ld, size / 2, alpha, beta, bias);
+    launch_k(lrn_kernel, bw_grid(pixels * c, 256), 256, 0, as_stream(stream), x, y, pixels, c, x_ld, y_ld, size / 2, alpha, beta, bias);
   }
   B200OV_LAUNCH_CHECK("lrn_kernel");
   return B200OV_OK;

@@ -190,7 +190,7 @@ static int launch_transpose_st(const TIN* x, TOUT* y, int batch, int rows, int c
   const long long blocks = (long long)batch * tiles_r * tiles_c;
   if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "transpose: grid too large");
   if (blocks == 0) return B200OV_OK;
-  transpose_kernel<false, TIN, TOUT><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr, 0.f, 0,
+  launch_k(transpose_kernel<false, TIN, TOUT>, (unsigned)blocks, 256, 0, s, x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr, 0.f, 0,
                                                                      nullptr, 0.f);
   B200OV_LAUNCH_CHECK("transpose_kernel");
   return B200OV_OK;
@@ -204,10 +204,10 @@ static int launch_transpose(bool affine, const float* x, float* y, int batch, in
   if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "transpose: grid too large");
   if (blocks == 0) return B200OV_OK;
   if (affine)
-    transpose_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, has_scale,
+    launch_k(transpose_kernel<true>, (unsigned)blocks, 256, 0, s, x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, has_scale,
                                                            scale_vec, scale_s, has_shift, shift_vec, shift_s);
   else
-    transpose_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr,
+    launch_k(transpose_kernel<false>, (unsigned)blocks, 256, 0, s, x, y, rows, cols, x_ld, y_ld, tiles_r, tiles_c, 0, nullptr,
                                                             0.f, 0, nullptr, 0.f);
   B200OV_LAUNCH_CHECK("transpose_kernel");
   return B200OV_OK;
@@ -220,20 +220,20 @@ static int input_to_nhwc_typed(const TIN* x, float* y, int n, int c, int hw, int
     const long long pixels = (long long)n * hw;
     if constexpr (sizeof(TIN) == 1) {
       if (y_ld == 4 && aligned16(y) && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3u) == 0) {
-        nchw8_to_nhwc4_x4_kernel<TIN><<<bw_grid(pixels / 4, 256), 256, 0, s>>>(x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
+        launch_k(nchw8_to_nhwc4_x4_kernel<TIN>, bw_grid(pixels / 4, 256), 256, 0, s, x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
                                                                               has_shift, shift_vec, shift_s);
         B200OV_LAUNCH_CHECK("nchw8_to_nhwc4_x4_kernel");
         return B200OV_OK;
       }
     }
     if (y_ld == 8 && aligned16(y))
-      nchw_to_nhwc_smallc_kernel<4, 8, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+      launch_k(nchw_to_nhwc_smallc_kernel<4, 8, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
                                                                                 scale_s, has_shift, shift_vec, shift_s);
     else if (y_ld == 4 && aligned16(y))
-      nchw_to_nhwc_smallc_kernel<4, 4, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+      launch_k(nchw_to_nhwc_smallc_kernel<4, 4, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
                                                                                 scale_s, has_shift, shift_vec, shift_s);
     else
-      nchw_to_nhwc_smallc_kernel<4, 0, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
+      launch_k(nchw_to_nhwc_smallc_kernel<4, 0, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
                                                                                 scale_s, has_shift, shift_vec, shift_s);
     B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
     return B200OV_OK;
@@ -241,7 +241,7 @@ static int input_to_nhwc_typed(const TIN* x, float* y, int n, int c, int hw, int
   const int tiles_r = ceil_div(c, 32), tiles_c = ceil_div(hw, 32);
   const long long blocks = (long long)n * tiles_r * tiles_c;
   if (blocks > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "input_to_nhwc: grid too large");
-  transpose_kernel<true, TIN><<<(unsigned)blocks, 256, 0, s>>>(x, y, c, hw, hw, y_ld, tiles_r, tiles_c, has_scale, scale_vec,
+  launch_k(transpose_kernel<true, TIN>, (unsigned)blocks, 256, 0, s, x, y, c, hw, hw, y_ld, tiles_r, tiles_c, has_scale, scale_vec,
                                                               scale_s, has_shift, shift_vec, shift_s);
   B200OV_LAUNCH_CHECK("transpose_kernel");
   return B200OV_OK;
@@ -251,7 +251,7 @@ template <typename TIN>
 static int input_to_nhwc_split_typed(const TIN* x, float* y, int n, int c, int hw, int has_scale, const float* scale_vec, float scale_s,
                                      int has_shift, const float* shift_vec, float shift_s, cudaStream_t s) {
   const long long pixels = (long long)n * hw;
-  nchw_to_nhwc_smallc_kernel<4, 44, TIN><<<bw_grid(pixels, 256), 256, 0, s>>>(x, y, pixels, c, hw, 4, has_scale, scale_vec, scale_s,
+  launch_k(nchw_to_nhwc_smallc_kernel<4, 44, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, 4, has_scale, scale_vec, scale_s,
                                                                             has_shift, shift_vec, shift_s);
   B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
   return B200OV_OK;
@@ -344,9 +344,9 @@ int b200ov_copy2d_st(const void* src, int src_dtype, void* dst, int dst_dtype, i
       (reinterpret_cast<uintptr_t>(dst) & 3u) == 0)       // half -> half: a float copy of half the width
     return b200ov_copy2d(static_cast<const float*>(src), static_cast<float*>(dst), rows, cols / 2, src_ld / 2, dst_ld / 2, stream);
   const int g = bw_grid(rows * cols, 256);
-  if (sh && dh) copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
-  else if (sh) copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(src), static_cast<float*>(dst), rows, cols, src_ld, dst_ld);
-  else copy2d_cast_kernel<<<g, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
+  if (sh && dh) launch_k(copy2d_cast_kernel<__half, __half>, g, 256, 0, s, static_cast<const __half*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
+  else if (sh) launch_k(copy2d_cast_kernel<__half, float>, g, 256, 0, s, static_cast<const __half*>(src), static_cast<float*>(dst), rows, cols, src_ld, dst_ld);
+  else launch_k(copy2d_cast_kernel<float, __half>, g, 256, 0, s, static_cast<const float*>(src), static_cast<__half*>(dst), rows, cols, src_ld, dst_ld);
   B200OV_LAUNCH_CHECK("copy2d_cast_kernel");
   return B200OV_OK;
 }
@@ -358,9 +358,9 @@ int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream
   const int g = bw_grid(count, 256);
   switch (dtype) {
     case B200OV_DT_F32: B200OV_CUDA(cudaMemcpyAsync(y, x, (size_t)count * 4, cudaMemcpyDeviceToDevice, s)); return B200OV_OK;
-    case B200OV_DT_F16: widen_kernel<<<g, 256, 0, s>>>(static_cast<const __half*>(x), y, count); break;
-    case B200OV_DT_U8: widen_kernel<<<g, 256, 0, s>>>(static_cast<const uint8_t*>(x), y, count); break;
-    case B200OV_DT_I8: widen_kernel<<<g, 256, 0, s>>>(static_cast<const int8_t*>(x), y, count); break;
+    case B200OV_DT_F16: launch_k(widen_kernel<__half>, g, 256, 0, s, static_cast<const __half*>(x), y, count); break;
+    case B200OV_DT_U8: launch_k(widen_kernel<uint8_t>, g, 256, 0, s, static_cast<const uint8_t*>(x), y, count); break;
+    case B200OV_DT_I8: launch_k(widen_kernel<int8_t>, g, 256, 0, s, static_cast<const int8_t*>(x), y, count); break;
     default: return set_error(B200OV_ERR_INVALID, "widen: unknown element type %d", dtype);
   }
   B200OV_LAUNCH_CHECK("widen_kernel");
@@ -372,8 +372,8 @@ int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_
   if (rows == 0) return B200OV_OK;
   const bool vec = (cols % 4 == 0) && (src_ld % 4 == 0) && (dst_ld % 4 == 0) && aligned16(src) && aligned16(dst);
   cudaStream_t s = as_stream(stream);
-  if (vec) copy2d_kernel<4><<<bw_grid(rows * (cols / 4), 256), 256, 0, s>>>(src, dst, rows, cols, src_ld, dst_ld);
-  else copy2d_kernel<1><<<bw_grid(rows * cols, 256), 256, 0, s>>>(src, dst, rows, cols, src_ld, dst_ld);
+  if (vec) launch_k(copy2d_kernel<4>, bw_grid(rows * (cols / 4), 256), 256, 0, s, src, dst, rows, cols, src_ld, dst_ld);
+  else launch_k(copy2d_kernel<1>, bw_grid(rows * cols, 256), 256, 0, s, src, dst, rows, cols, src_ld, dst_ld);
   B200OV_LAUNCH_CHECK("copy2d_kernel");
   return B200OV_OK;
 }

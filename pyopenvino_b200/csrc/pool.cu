@@ -160,7 +160,7 @@ struct PoolTmaP {
 constexpr int POOL_TMA_CONSUMERS = 512;                     // 16 consumer warps
 constexpr int POOL_TMA_THREADS = POOL_TMA_CONSUMERS + 32;   // + the TMA producer warp
 constexpr int POOL_TMA_STAGES = 4;
-constexpr int POOL_TMA_BUDGET = 48 * 1024, POOL_TMA_STAGE_CAP = 54 * 1024;     // bytes per stage: target / hard limit (4 stages < 227 KB)
+constexpr int POOL_TMA_STAGE_BYTES = 56 * 1024;       // per stage; 4 stages + barriers < 227 KB
 
 template <int K, int S, typename T>
 __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const PoolTmaP p, const __grid_constant__ CUtensorMap map_x,
@@ -283,36 +283,18 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
 
 // Tile geometry for the TMA kernel; false when the shape does not fit (the strip / generic kernels take over).
 static bool pool_tma_plan(const b200ov_pool_desc* d, PoolTmaP& q, int esize) {
-  const int K = d->kh, S = d->sh;
-  const int cb = 32 * esize;                      // bytes of one pixel's 32-channel chunk
-  if (d->ow <= 0 || d->oh <= 0) return false;
-  const int col_tiles = ceil_div(d->ow, 32);
-  q.tw = ceil_div(d->ow, col_tiles);
-  q.nimg = 32 / q.tw;
-  if (q.nimg > d->n) q.nimg = d->n;
-  if (q.nimg < 1) q.nimg = 1;
-  q.bw = (q.tw - 1) * S + K;
-  const int budget = POOL_TMA_BUDGET;
-  int tr = d->oh;
-  while (tr > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
-  if (q.nimg > 1 && q.nimg * ((tr - 1) * S + K) * q.bw * cb > budget) {       // several images do not fit even one row
-    q.nimg = 1;
-    tr = d->oh;
-    while (tr > 1 && ((tr - 1) * S + K) * q.bw * cb > budget) --tr;
-  }
-  const int row_tiles = ceil_div(d->oh, tr);
-  q.tr = ceil_div(d->oh, row_tiles);
-  q.bh = (q.tr - 1) * S + K;
-  q.box_bytes = q.nimg * q.bh * q.bw * cb;
-  q.stage_bytes = round_up(q.box_bytes, 128);
-  if (q.stage_bytes > POOL_TMA_STAGE_CAP || q.bw > 256 || q.bh > 256) return false;
+  tma::TilePlan t;
+  if (!tma::plan_tiles(d->n, d->oh, d->ow, d->kh, d->sh, 32 * esize, POOL_TMA_STAGE_BYTES, t)) return false;
+  q.tw = t.tw; q.tr = t.tr; q.nimg = t.nimg; q.bw = t.bw; q.bh = t.bh;
+  q.box_bytes = t.box_bytes;
+  q.stage_bytes = round_up(t.box_bytes, 128);
   const int cchunks = ceil_div(d->c, 32), img_groups = ceil_div(d->n, q.nimg);
-  const long long items = (long long)img_groups * row_tiles * col_tiles * cchunks;
+  const long long items = (long long)img_groups * t.row_tiles * t.col_tiles * cchunks;
   if (items <= 0 || items > 0x7fffffffLL) return false;
   q.items = (uint32_t)items;
   q.n = d->n; q.c = d->c; q.oh = d->oh; q.ow = d->ow; q.y_ld = d->y_ld; q.pt = d->pt; q.pl = d->pl;
   q.hp = d->h + d->pt + d->pb; q.wpad = d->w + d->pl + d->pr;
-  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(col_tiles); q.d_rowtiles = FastDiv(row_tiles); q.d_tw = FastDiv(q.tw);
+  q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(t.col_tiles); q.d_rowtiles = FastDiv(t.row_tiles); q.d_tw = FastDiv(q.tw);
   return true;
 }
 
@@ -320,14 +302,14 @@ template <int K, int S, typename T>
 static int launch_pool_tma(const PoolTmaP& q, const CUtensorMap& map, const float* scale, const float* shift, T* y, cudaStream_t s) {
   auto kern = pool_max_tma_kernel<K, S, T>;
   static bool configured = false;
-  const int smem = POOL_TMA_STAGES * POOL_TMA_STAGE_CAP + 16 * POOL_TMA_STAGES + 256;
+  const int smem = POOL_TMA_STAGES * POOL_TMA_STAGE_BYTES + 16 * POOL_TMA_STAGES + 256;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int need = POOL_TMA_STAGES * q.stage_bytes + 16 * POOL_TMA_STAGES + 256;
   const int grid = (int)(q.items < (uint32_t)props().sm_count ? q.items : (uint32_t)props().sm_count);
-  kern<<<grid, POOL_TMA_THREADS, need, s>>>(q, map, scale, shift, y);
+  launch_k(kern, grid, POOL_TMA_THREADS, need, s, q, map, scale, shift, y);
   B200OV_LAUNCH_CHECK("pool_max_tma_kernel");
   return B200OV_OK;
 }
@@ -440,7 +422,7 @@ static int pool2d_f16(const b200ov_pool_desc* d, const __half* x, const float* s
   }
   PoolP p{d->n, d->h, d->w, d->c, d->kh, d->kw, d->sh, d->sw, d->pt, d->pl, d->pb, d->pr, d->oh, d->ow, d->x_ld, d->y_ld, d->mode};
   const long long total = (long long)d->n * d->oh * d->ow * (d->c / 4);
-  pool_kernel<4, __half><<<bw_grid(total, 256), 256, 0, s>>>(p, x, scale, shift, y);
+  launch_k(pool_kernel<4, __half>, bw_grid(total, 256), 256, 0, s, p, x, scale, shift, y);
   B200OV_LAUNCH_CHECK("pool_kernel");
   return B200OV_OK;
 }
@@ -504,8 +486,8 @@ extern "C" int b200ov_pool2d(const b200ov_pool_desc* d, const void* x_raw, const
   }
   long long total = (long long)d->n * d->oh * d->ow * (vec ? d->c / 4 : d->c);
   int grid = bw_grid(total, 256);
-  if (vec) pool_kernel<4, float><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
-  else pool_kernel<1, float><<<grid, 256, 0, as_stream(stream)>>>(p, x, scale, shift, y);
+  if (vec) launch_k(pool_kernel<4, float>, grid, 256, 0, as_stream(stream), p, x, scale, shift, y);
+  else launch_k(pool_kernel<1, float>, grid, 256, 0, as_stream(stream), p, x, scale, shift, y);
   B200OV_LAUNCH_CHECK("pool_kernel");
   return B200OV_OK;
 }

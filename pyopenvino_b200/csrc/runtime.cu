@@ -37,6 +37,16 @@ const DeviceProps& props() {
   return g_props;
 }
 
+// Programmatic dependent launch is opt-in (B200OV_PDL=1): see common.cuh.
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200OV_PDL");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 }  // namespace b200ov
 
 using namespace b200ov;
