@@ -173,7 +173,7 @@ def kernel_of(kind):
     """layer family -> the CUDA kernel that runs it"""
     if kind.startswith('conv') or kind == 'matmul':
         return 'conv_f16x2_kernel'
-    return {'depthwise': 'dwconv3x3_strip_kernel', 'maxpool': 'pool_max_strip_kernel', 'lrn': 'lrn_vec4_kernel',
+    return {'depthwise': 'dwconv3x3_tma_kernel', 'maxpool': 'pool_max_tma_kernel', 'lrn': 'lrn_vec4_kernel',
             'input_layout': 'nchw_to_nhwc_smallc_kernel'}.get(kind, kind)
 
 
@@ -251,8 +251,18 @@ def time_e2e(exe, in_name, out_name, x, steps, warmup, world, dtype=np.float32):
     bufs = [exe.request_buffer(s, in_name, dtype) for s in range(nreq)]
     for b in bufs:
         b[...] = x
+    # The all-gather of the result rows runs on its own stream: queued on the engine's stream it would sit behind the NEXT
+    # request's kernels, and its (pageable) upload would block the host until they finish -- the H2D of the request after
+    # that could then no longer overlap anything (round-2 finding: 8.9 ms per step at 8 GPUs = H2D + kernels in series).
+    side = torch.cuda.Stream() if world > 1 else None
+
+    def gather(res):
+        if world > 1:
+            with torch.cuda.stream(side):
+                distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
+
     for i in range(max(warmup, 1)):
-        exe.wait(exe.start_async({in_name: bufs[i % nreq]}, slot=i % nreq))
+        gather(exe.wait(exe.start_async({in_name: bufs[i % nreq]}, slot=i % nreq)))
     torch.cuda.synchronize()
     distributed.barrier()
     t0 = time.perf_counter()
@@ -261,12 +271,10 @@ def time_e2e(exe, in_name, out_name, x, steps, warmup, world, dtype=np.float32):
         slot = exe.start_async({in_name: bufs[i % nreq]}, slot=i % nreq)
         if pending is not None:
             res = exe.wait(pending)
-            if world > 1:
-                distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
+            gather(res)
         pending = slot
     res = exe.wait(pending)
-    if world > 1:
-        distributed.gather_outputs(torch.from_numpy(res[out_name]).cuda(non_blocking=True))
+    gather(res)
     torch.cuda.synchronize()
     return distributed.max_over_ranks(time.perf_counter() - t0), res[out_name]
 
@@ -379,7 +387,7 @@ def measure(model, batch, desc, args, peaks, rank, world, local, primary, storag
     top_kind = max(kern, key=lambda k: kern[k]['ms'])
     res['roofline'] = kernel_roofline(top_kind, kern[top_kind], total_ms, peaks, model)
     res['kernel_rooflines'] = {k: kernel_roofline(k, v, total_ms, peaks, model) for k, v in kern.items()
-                               if k in ('conv_f16x2_kernel', 'dwconv3x3_strip_kernel', 'pool_max_strip_kernel', 'lrn_vec4_kernel')
+                               if k in ('conv_f16x2_kernel', 'dwconv3x3_tma_kernel', 'pool_max_tma_kernel', 'lrn_vec4_kernel')
                                and k != top_kind and v['ms'] > 0}
     model_roof_ms = sum(l['roofline_ms'] for l in layers)
     res['model_roofline'] = {'sum_layer_roofline_ms': model_roof_ms, 'frac': model_roof_ms / ms_step,

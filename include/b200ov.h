@@ -112,7 +112,17 @@ typedef struct {
   int32_t math;                /* B200OV_MATH_*                                                  */
   int32_t x_dtype, y_dtype;    /* storage type of x / y: B200OV_DT_F32 (0, default) or B200OV_DT_F16; F16 needs the
                                   B200OV_MATH_F16X2 path (an FP16 input IS its own hi part: 2 MMAs per product)  */
+  int32_t pre_pool;            /* B200OV_PREPOOL_*: an operator applied to x on the way into the contraction, so that its
+                                  result never exists in memory (the 3x3 stride-1 MaxPool in front of an inception
+                                  module's pool_proj 1x1 convolution)                                             */
 } b200ov_conv_desc;
+
+/* pre_pool values.  MAX3X3S1: x is first passed through MaxPool kernel 3x3, strides 1, pads_begin = pads_end = 1 with the
+ * reference's window rule (zero padding takes part in the max, MaxPool.py:41-72); needs a 1x1 / stride-1 / unpadded
+ * convolution of FP32 feature maps on the B200OV_MATH_F16X2 path (B200OV_ERR_UNSUPPORTED otherwise: the caller then
+ * issues b200ov_pool2d + b200ov_conv2d).  The result is bit-identical to those two calls. */
+#define B200OV_PREPOOL_NONE 0
+#define B200OV_PREPOOL_MAX3X3S1 1
 
 /* OIHW -> packed [kh*kw*cin (pad 16)][ldw] (row index ordered ky, kx, ci).  `ldw` and the row
  * count come from b200ov_conv_weight_dims(); `w_packed` must hold `total_floats`.  Replaces `kernel.reshape(kn,-1).T`, Convolution.py:83. */

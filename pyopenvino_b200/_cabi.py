@@ -23,7 +23,11 @@ class B200ovError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'cin', 'cout', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
                                          'x_ld', 'y_ld', 'ldw', 'act')] + \
-               [('act_lo', C.c_float), ('act_hi', C.c_float), ('math', C.c_int32), ('x_dtype', C.c_int32), ('y_dtype', C.c_int32)]
+               [('act_lo', C.c_float), ('act_hi', C.c_float), ('math', C.c_int32), ('x_dtype', C.c_int32), ('y_dtype', C.c_int32),
+                ('pre_pool', C.c_int32)]
+
+
+PREPOOL_NONE, PREPOOL_MAX3X3S1 = 0, 1
 
 
 class DwConvDesc(C.Structure):

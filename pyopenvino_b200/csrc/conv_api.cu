@@ -57,6 +57,14 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const void* x_raw, const float* w_p
   int rc = validate(d, x_raw, w_packed, y_raw);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
+  if (d->pre_pool != B200OV_PREPOOL_NONE) {
+    // the fused MaxPool lives in the f16x2 contraction's A producers only; no other kernel may silently drop it
+    B200OV_REQUIRE(d->pre_pool == B200OV_PREPOOL_MAX3X3S1, "conv2d: unknown pre_pool %d", d->pre_pool);
+    if ((d->math != B200OV_MATH_AUTO && d->math != B200OV_MATH_F16X2) || d->x_dtype != B200OV_DT_F32 || d->y_dtype != B200OV_DT_F32 ||
+        !f16x2_eligible(d, x_raw))
+      return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool needs the f16x2 path on FP32 feature maps");
+    return conv2d_f16x2(d, x_raw, f16_section(d, w_packed), bias, y_raw, s);
+  }
   if (d->x_dtype != B200OV_DT_F32 || d->y_dtype != B200OV_DT_F32) {
     // FP16 feature maps: only the f16x2 contraction reads / writes them
     B200OV_REQUIRE((d->x_dtype == B200OV_DT_F32 || d->x_dtype == B200OV_DT_F16 || d->x_dtype == B200OV_DT_HL) &&

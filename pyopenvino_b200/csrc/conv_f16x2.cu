@@ -109,6 +109,11 @@ struct Params {
   // [ks * num_slots, (ks + 1) * num_slots) of the K range (num_slots = slots per split, even) and writes its raw partial
   // sums to rows [ks * ws_rows + m, ...) of the workspace, which a second kernel reduces in a fixed order.
   int ksplit, ws_rows;
+  // POOL variant (1x1 convolution of MaxPool3x3/s1/p1(x)): per slot, the 128 tile pixels plus a halo of w + 1 pixels on either
+  // side of their linear NHW range (pool_rows = 128 + 2w + 2 rows of 32 channels = 128 bytes) are staged in shared memory
+  // by TMA from the [pixels][channels] view of x, in a ring of pool_stages stages of pool_stage_bytes.
+  int pool_rows, pool_stage_bytes, pool_stages;
+  FastDiv d_pool_stages;
   int a_hl;                            // 1: x already holds the FP16 (hi, scaled lo) pairs (network input written by the layout
                                        //    kernel, b200ov_input_to_nhwc_split): the producers only route words, no split
   FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots, d_ksplit;
@@ -157,6 +162,10 @@ struct Smem {
   static constexpr int NUM_BARS = 2 * SB + 2 * A_SLOTS + 8;
   static constexpr int TMEM_PTR = BARS + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR + 16 + 1024;                   // + slack for the 1024-byte alignment of the base
+  // POOL variant only: full[8] / empty[8] barriers of the pixel-tile ring, then the ring itself (1024-byte aligned stages)
+  static constexpr int POOL_BARS = TMEM_PTR + 16;
+  static constexpr int POOL_RING = (POOL_BARS + 16 * 8 + 1023) / 1024 * 1024;
+  static constexpr int POOL_MAX_STAGES = 8;
 };
 
 __device__ __forceinline__ constexpr uint32_t instr_desc(int block_n) {
@@ -241,12 +250,15 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
 }
 
 // A16: the input feature map is stored as FP16 (a == a_hi: no split, 4 MMAs per slot); O16: the output is stored as FP16.
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16>
+// POOL: 1x1 convolution of MaxPool3x3/s1/p1(x) (b200ov_conv_desc.pre_pool): the producers take the 9-tap max of every
+// 8-channel run before the split, so the pooled tensor never exists (MaxPool.py:41-72: the zero padding takes part).
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* __restrict__ bias,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_y0,
-                  const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2) {
+                  const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2,
+                  const __grid_constant__ CUtensorMap map_x) {
   using L = Smem<BLOCK_N, SB>;
   constexpr int A_SLOTS = a_slots(BLOCK_N);
   constexpr int A_COL0 = a_col0(BLOCK_N);
@@ -271,6 +283,8 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
   auto bar_cross_full = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 4 + i); };
   auto bar_cross_empty = [&](int i) { return base + L::BARS + 8 * (2 * SB + 2 * A_SLOTS + 6 + i); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_PTR);
+  auto bar_pool_full = [&](int s) { return base + L::POOL_BARS + 8 * s; };
+  auto bar_pool_empty = [&](int s) { return base + L::POOL_BARS + 8 * (L::POOL_MAX_STAGES + s); };
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // broadcast: tells ptxas the role branches are warp-uniform
@@ -290,6 +304,13 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_cross_full(i), 1);
       mbar_init(bar_cross_empty(i), NUM_EPILOGUE);
+    }
+    if constexpr (POOL) {
+      for (int i = 0; i < p.pool_stages; ++i) {
+        mbar_init(bar_pool_full(i), 1);
+        mbar_init(bar_pool_empty(i), SET_THREADS);
+      }
+      prefetch_tensormap(&map_x);
     }
     fence_mbar_init();
     prefetch_tensormap(&map_hi);
@@ -437,6 +458,27 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           if ((slot + 2) % CHUNK == 0 || last) ++chunkcount;
         }
       }
+    } else if constexpr (POOL) {
+      // ================= pixel-tile loader (POOL variant; this warp idles otherwise) ===================
+      // One TMA box per slot: 32 channels x pool_rows consecutive pixels starting w + 1 pixels before the tile's first
+      // pixel (rows outside the tensor arrive as zeros; the producers never use them).
+      int st = 0;
+      uint32_t phase = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
+        uint32_t m_blk_, n_blk_, ksp_;
+        tile_coord(p, tile, m_blk_, n_blk_, ksp_);
+        const int r0 = (int)m_blk_ * BLOCK_M - p.w - 1;
+        for (int slot = 0; slot < p.num_slots; ++slot) {
+          mbar_wait(bar_pool_empty(st), phase ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bar_pool_full(st), (uint32_t)p.pool_rows * 128u);
+            tma_load_2d(base + L::POOL_RING + st * p.pool_stage_bytes, &map_x, slot * SLOT_K, r0, bar_pool_full(st));
+          }
+          __syncwarp();
+          if (++st == p.pool_stages) { st = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp < W_EPILOGUE0) {
     // ================= A producers: gather -> split -> TMEM ==========================================
@@ -454,6 +496,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     const TA* x = reinterpret_cast<const TA*>(x_raw);
     const TA* rbase[4];
     int riy[4], rix[4];
+    int prow[4], pflag[4];             // POOL: box row of the window centre; bits: 1 up, 2 down, 4 left, 8 right neighbour inside the image, 16 row < M
     uint32_t cur_tl = 0xffffffffu, cur_slot0 = 0;
     F16_TRACE_DECL
     auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
@@ -475,11 +518,53 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           riy[r] = m < p.M ? (int)oy * p.sh - p.pt : -(1 << 28);      // a row past M never passes the bounds test
           rix[r] = (int)ox * p.sw - p.pl;
           rbase[r] = x + ((long long)((int)img * p.h + riy[r]) * p.w + rix[r]) * p.x_ld;
+          if constexpr (POOL) {
+            prow[r] = (m - m0) + p.w + 1;
+            pflag[r] = m < p.M ? (16 | (oy > 0 ? 1 : 0) | ((int)oy + 1 < p.h ? 2 : 0) | (ox > 0 ? 4 : 0) | ((int)ox + 1 < p.w ? 8 : 0)) : 0;
+          }
         }
       }
       const uint32_t unit = (cur_slot0 + slot) * 4 + u4;
       const bool uvalid = unit < (uint32_t)p.units;
-      if constexpr (!PAIR) {
+      if constexpr (POOL) {
+        // 1x1 convolution (one tap, a slot = 32 channels) of the 3x3 / stride 1 / pad 1 max-pooled map, taken from the slot's
+        // pixel tile in shared memory (TMA, 128B swizzle: 16-byte chunk c of box row r sits at chunk c ^ (r & 7)).  A tap
+        // outside the image is aliased to the window centre (max is idempotent) and the reference's zero padding enters as
+        // one max with 0 for border pixels (MaxPool.py:41-72); rows past M produce zeros.
+        uint32_t round, st;
+        p.d_pool_stages.divmod(item, round, st);
+        mbar_wait(bar_pool_full(st), round & 1);
+        const uint32_t sbase = base + L::POOL_RING + st * p.pool_stage_bytes;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int f = pflag[r];
+          const int oy0 = (f & 1) ? -p.w : 0, oy2 = (f & 2) ? p.w : 0, ox0 = (f & 4) ? -1 : 0, ox2 = (f & 8) ? 1 : 0;
+          const float edge = (f & 15) == 15 ? -INFINITY : 0.f;
+          float mx[8];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int rowy = prow[r] + (dy == 0 ? oy0 : (dy == 1 ? 0 : oy2));
+            float4 t[3][2];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int row = rowy + (dx == 0 ? ox0 : (dx == 1 ? 0 : ox2));
+              const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4) ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dx][0].x), "=f"(t[dx][0].y), "=f"(t[dx][0].z), "=f"(t[dx][0].w) : "r"(a));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dx][1].x), "=f"(t[dx][1].y), "=f"(t[dx][1].z), "=f"(t[dx][1].w) : "r"(a ^ 16u));
+            }
+            float rowmax[8];
+            rowmax[0] = fmaxf(fmaxf(t[0][0].x, t[1][0].x), t[2][0].x); rowmax[1] = fmaxf(fmaxf(t[0][0].y, t[1][0].y), t[2][0].y);
+            rowmax[2] = fmaxf(fmaxf(t[0][0].z, t[1][0].z), t[2][0].z); rowmax[3] = fmaxf(fmaxf(t[0][0].w, t[1][0].w), t[2][0].w);
+            rowmax[4] = fmaxf(fmaxf(t[0][1].x, t[1][1].x), t[2][1].x); rowmax[5] = fmaxf(fmaxf(t[0][1].y, t[1][1].y), t[2][1].y);
+            rowmax[6] = fmaxf(fmaxf(t[0][1].z, t[1][1].z), t[2][1].z); rowmax[7] = fmaxf(fmaxf(t[0][1].w, t[1][1].w), t[2][1].w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx[i] = dy == 0 ? fmaxf(rowmax[i], edge) : fmaxf(mx[i], rowmax[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[r].v[i] = (f & 16) ? mx[i] : 0.f;
+        }
+        mbar_arrive(bar_pool_empty(st));                 // every value of the stage this thread needs is in its registers
+      } else if constexpr (!PAIR) {
         uint32_t tap, cu, ky, kx;
         p.d_upt.divmod(unit, tap, cu);
         p.d_kw.divmod(tap, ky, kx);
@@ -816,18 +901,31 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
   return B200OV_OK;
 }
 
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16>
-static int launch(const Params& p, const void* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
-                  const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s) {
+constexpr int MAX_SMEM = 227 * 1024;
+
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false>
+static int launch(const Params& p0, const void* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
+                  const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s, const CUtensorMap* mx = nullptr) {
   using L = Smem<BLOCK_N, SB>;
-  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR, A16, O16>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR, A16, O16, POOL>;
   static bool configured = false;
   if (!configured) {
-    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL ? MAX_SMEM : L::TOTAL));
     configured = true;
   }
+  Params p = p0;
+  int smem = L::TOTAL;
+  if constexpr (POOL) {
+    // the pixel-tile ring takes what the weight ring and the output staging leave of the SM's shared memory
+    int stages = (MAX_SMEM - 1024 - L::POOL_RING) / p.pool_stage_bytes;
+    if (stages > L::POOL_MAX_STAGES) stages = L::POOL_MAX_STAGES;
+    if (stages < 2) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool tile ring does not fit in shared memory");
+    p.pool_stages = stages;
+    p.d_pool_stages = FastDiv(stages);
+    smem = L::POOL_RING + stages * p.pool_stage_bytes + 1024;
+  }
   const int grid = p.num_tiles < props().sm_count ? p.num_tiles : props().sm_count;
-  launch_k(kern, grid, NUM_THREADS, L::TOTAL, s, p, x, bias, status, mh, ml, my[0], my[1], my[2]);
+  launch_k(kern, grid, NUM_THREADS, smem, s, p, x, bias, status, mh, ml, my[0], my[1], my[2], mx != nullptr ? *mx : mh);
   B200OV_LAUNCH_CHECK("conv_f16x2_kernel");
   return B200OV_OK;
 }
@@ -992,6 +1090,11 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
   // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1.
   { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
+  const bool pool = d->pre_pool == B200OV_PREPOOL_MAX3X3S1;
+  if (d->pre_pool != B200OV_PREPOOL_NONE &&
+      !(pool && d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 && d->pl == 0 && d->oh == d->h && d->ow == d->w &&
+        d->x_dtype == B200OV_DT_F32 && !o16 && d->cin % 8 == 0 && ksplit == 1))
+    return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool needs a 1x1 / stride-1 / unpadded convolution of FP32 feature maps");
   p.a_hl = d->x_dtype == B200OV_DT_HL ? 1 : 0;
   if (p.a_hl && p.pair4) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: a pre-split input needs the super-pixel stem path");
   p.wide_loads = !a16 && !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
@@ -1014,6 +1117,20 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
     }
   }
   unsigned int* status = f16x2_status_word();
+  if (pool) {
+    // [pixels][channels] view of x; box = 32 channels x (128 + 2w + 2) pixels, 128B swizzle, zeros outside the tensor
+    p.pool_rows = f16::BLOCK_M + 2 * d->w + 2;
+    if (p.pool_rows > 256) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool needs an image width of at most 63 pixels");
+    p.pool_stage_bytes = round_up(p.pool_rows * 128, 1024);
+    CUtensorMap mx;
+    rc = f16::make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, d->cin, (long long)p.M, (long long)d->x_ld * 4, f16::SLOT_K, p.pool_rows);
+    if (rc) return rc;
+    // a two-stage weight ring leaves room for the pixel tiles (the layer is bandwidth-bound: the MMA warp never waits on B)
+    if (block_n == 128) return f16::launch<128, 2, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+    if (block_n == 96) return f16::launch<96, 2, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+    if (block_n == 64) return f16::launch<64, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+    return f16::launch<32, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+  }
 #define B200OV_F16_LAUNCH2(N_, SB_, W_, P_, A_) \
   (o16 ? f16::launch<N_, SB_, W_, P_, A_, true>(p, x, bias, status, mh, ml, my, s) \
        : f16::launch<N_, SB_, W_, P_, A_, false>(p, x, bias, status, mh, ml, my, s))

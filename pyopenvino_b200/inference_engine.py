@@ -247,7 +247,9 @@ class _Liveness:
 
     def _consumers(self, node_id):
         G, plan = self.exe.ienet.G, self.exe._plan
-        return sum(1 for s in G.successors(node_id) if not plan[s]['skip'] and not plan[s].get('const_done'))
+        # a MaxPool folded into its consumer ('pool_into') still reads its input -- through that consumer's step
+        return sum(1 for s in G.successors(node_id)
+                   if (not plan[s]['skip'] or plan[s].get('pool_into') is not None) and not plan[s].get('const_done'))
 
     def stored(self, node_id, data):
         """`data` was stored as the output of graph node `node_id`."""
@@ -266,7 +268,11 @@ class _Liveness:
     def consumed(self, task):
         """Step `task` has been queued: its inputs have one consumer less."""
         G = self.exe.ienet.G
-        for pred in G.pred[task]:
+        preds = list(G.pred[task])
+        pooled = self.exe._plan[task]['ops'].get('pre_pool')
+        if pooled is not None:
+            preds += list(G.pred[pooled])
+        for pred in preds:
             key = self.node_chunk.get(pred)
             if key is None:
                 continue
@@ -467,6 +473,33 @@ class Executable_Network:
                     if G.edges[(tail, nxt)]['connection'][3] == 0 and common_def.string_to_tuple(cd['strides'])[1] % 2 == 0 and \
                             out_dims[3] % 2 == 0 and common_def.string_to_tuple(cd['dilations']) == (1, 1):
                         ops['split'] = True
+        # MaxPool 3x3 / stride 1 / pads 1 whose only consumer is a 1x1 convolution (the pool -> pool_proj pair of an inception
+        # module): the convolution's A producers take the 9-tap max on the way in (b200ov_conv_desc.pre_pool), so the pooled
+        # tensor is neither written nor re-read.  FP32 storage only; bit-identical to the two separate kernels.
+        if self.storage == 'f32' and os.environ.get('B200OV_NO_POOL_FUSE') != '1':
+            for n in self.task_list:
+                node = G.nodes[n]
+                if node['type'] != 'MaxPool' or plan[n]['skip'] or plan[n]['ops']:
+                    continue
+                d = node['data']
+                in_dims = node['input'][0]['dims']
+                out_dims = node['output'][common_def.first_output_port(node)]['dims']
+                if len(in_dims) != 4 or tuple(in_dims) != tuple(out_dims) or in_dims[1] % 8 != 0 or in_dims[3] > 63 or \
+                        common_def.string_to_tuple(d['kernel']) != (3, 3) or common_def.string_to_tuple(d['strides']) != (1, 1) or \
+                        common_def.string_to_tuple(d['pads_begin']) != (1, 1) or common_def.string_to_tuple(d['pads_end']) != (1, 1):
+                    continue
+                nxt = self._single_consumer(n)
+                if nxt is None or G.out_degree(n) != 1 or G.nodes[nxt]['type'] != 'Convolution' or plan[nxt]['skip']:
+                    continue
+                cd = G.nodes[nxt]['data']
+                wdims = G.nodes[nxt]['input'][1]['dims']
+                if G.edges[(n, nxt)]['connection'][3] != 0 or tuple(wdims[2:]) != (1, 1) or \
+                        common_def.string_to_tuple(cd['strides']) != (1, 1) or common_def.string_to_tuple(cd['pads_begin']) != (0, 0) or \
+                        common_def.string_to_tuple(cd['pads_end']) != (0, 0) or common_def.string_to_tuple(cd['dilations']) != (1, 1):
+                    continue
+                plan[n]['skip'] = True
+                plan[n]['pool_into'] = nxt
+                plan[nxt]['ops']['pre_pool'] = n
         # Concat in place: producers whose only consumer is a channel Concat write into its buffer
         for n in self.task_list:
             node = G.nodes[n]
@@ -579,6 +612,8 @@ class Executable_Network:
             if step.get('const_done'):
                 continue
             inputs = self.prepare_inputs_for_task(task) if 'input' in node else {}
+            if 'pre_pool' in step['ops']:
+                inputs[0] = self.prepare_inputs_for_task(step['ops']['pre_pool'])[0]     # the folded MaxPool's own input
             fused = {}
             for key, val in step['ops'].items():
                 if key in ('bias', 'scale', 'shift'):

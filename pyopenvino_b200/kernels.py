@@ -271,7 +271,10 @@ def f16x2_ok(x, cin, act_code, mode):
     return x.ld % 4 == 0 and (cin % 8 == 0 or (cin <= 4 and x.ld == 4))
 
 
-def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None):
+def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None, pre_pool=False):
+    """`pre_pool`: x is the INPUT of a MaxPool 3x3 / stride 1 / pads 1 node whose only consumer is this 1x1 convolution; the
+    pooling runs inside the contraction's A producers (b200ov_conv_desc.pre_pool) where the f16x2 kernel takes the layer,
+    as a separate b200ov_pool2d otherwise (FP32-range re-run, FP16 storage, unaligned slices)."""
     x = as_nhwc(x)
     pk = w if isinstance(w, PackedWeights) else pack_conv(w)
     n, c, h, wd = x.shape
@@ -280,6 +283,13 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
     shape = (n, pk.cout, oh, ow)
     code, lo, hi = _act(act)
     mode = default_math if math is None else math
+    if pre_pool:
+        fusable = (x.st == 'f32' and f16x2_ok(x, c, code, mode) and c % 8 == 0 and (pk.kh, pk.kw) == (1, 1) and
+                   tuple(strides) == (1, 1) and tuple(pads_begin) == (0, 0) and (oh, ow) == (h, wd) and wd <= 63 and
+                   (out is None or out.st == 'f32') and pick_st(pk.cout) == 'f32')
+        if not fusable:
+            x = pool2d(x, _cabi.POOL_MAX, (3, 3), (1, 1), (1, 1), (1, 1), (h, wd))
+            pre_pool = False
     final = _check_out(out, shape) if out is not None else None
     if x.st == 'hl' and mode not in (_cabi.MATH_AUTO, _cabi.MATH_F16X2):
         raise _cabi.B200ovError('a pre-split network input can only feed the f16x2 contraction')
@@ -292,7 +302,8 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
         out = new_nhwc(*shape, st=pick_st(pk.cout) if half_ok else 'f32')
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=pk.cout, kh=pk.kh, kw=pk.kw, sh=strides[0], sw=strides[1],
                        pt=pads_begin[0], pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, ldw=pk.ldw,
-                       act=code, act_lo=lo, act_hi=hi, math=mode, x_dtype=x.code, y_dtype=out.code)
+                       act=code, act_lo=lo, act_hi=hi, math=mode, x_dtype=x.code, y_dtype=out.code,
+                       pre_pool=_cabi.PREPOOL_MAX3X3S1 if pre_pool else _cabi.PREPOOL_NONE)
     b = _vec_ptr(bias, pk.cout)
     _cabi.call('b200ov_conv2d', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(b), _p(out), _s())
     return _into(out, final)

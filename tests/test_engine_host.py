@@ -82,7 +82,8 @@ def test_rebatching_rewrites_every_dynamic_port(ie, model, batch, model_dir):
 
 def test_fusion_plan_census(ie, model_dir):
     """every Add / ReLU / Clamp / BN Multiply is absorbed by a producer."""
-    expect = {'mnist': 11, 'mnist_bn': 13, 'googlenet-v1': 86}
+    # GoogLeNet: 86 steps, nine of them 3x3 / stride-1 MaxPools that run inside the pool_proj convolution's producers
+    expect = {'mnist': 11, 'mnist_bn': 13, 'googlenet-v1': 77}
     for model, steps in expect.items():
         path = os.path.join(model_dir, model + '.xml')
         net = ie.read_network(path, None)
@@ -94,6 +95,15 @@ def test_fusion_plan_census(ie, model_dir):
         for t in ('Add', 'ReLU', 'Clamp', 'Multiply'):
             assert t not in types, (model, t)
         assert len(live) == steps, (model, len(live))
+        folded = [n for n in exe.task_list if plan[n].get('pool_into') is not None]
+        assert len(folded) == (9 if model == 'googlenet-v1' else 0)
+        for n in folded:
+            assert G.nodes[n]['type'] == 'MaxPool' and plan[plan[n]['pool_into']]['ops']['pre_pool'] == n
+    # FP16 storage keeps the pools as kernels of their own (half2 max there; the fused producer path is FP32-only)
+    net = ie.read_network(os.path.join(model_dir, 'googlenet-v1.xml'), None)
+    exe = ie.load_network(net, storage='f16')
+    plan = exe.build_plan()
+    assert not any(plan[n].get('pool_into') is not None for n in exe.task_list)
     net = ie.read_network(os.path.join(model_dir, 'ssd_mobilenet_v1_coco.xml'), None)
     exe = ie.load_network(net)
     plan = exe.build_plan()

@@ -1,0 +1,118 @@
+"""GPU parity of the producer-side fusions of the contraction kernel (round 2): the 3x3 / stride-1 MaxPool folded into
+the A producers of the 1x1 convolution that consumes it (b200ov_conv_desc.pre_pool; MaxPool.py:41-72 + Convolution.py:57-87)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import close
+
+pytestmark = pytest.mark.gpu
+
+POOL_DATA = {'strides': '1,1', 'kernel': '3,3', 'pads_begin': '1,1', 'pads_end': '1,1', 'rounding_type': 'ceil', 'auto_pad': 'explicit'}
+
+
+@pytest.mark.parametrize('shape', [
+    # n, cin, h, w, cout, act, sliced input / output
+    (3, 192, 28, 28, 32, ('relu',), False),       # inception_3a/pool -> pool_proj
+    (2, 480, 14, 14, 64, ('relu',), True),        # inception_4a, input = a channel slice of a wider buffer, output into a Concat slot
+    (5, 832, 7, 7, 128, ('relu',), False),        # inception_5a
+    (2, 528, 14, 14, 128, None, True),         # inception_4e
+    (1, 24, 5, 9, 40, None, False),            # odd map, C_out not a multiple of 32, K shorter than a slot
+    (2, 16, 1, 1, 8, ('relu',), False),           # 1x1 image: the window is all padding but the centre
+    (1, 8, 3, 63, 16, ('clamp', -0.5, 0.75), False),   # widest map the pixel-tile box covers (128 + 2w + 2 <= 256 rows)
+    (1, 8, 3, 200, 16, ('clamp', -0.5, 0.75), False),  # wider: kernels.conv2d issues the two kernels (1 + 1 launches)
+    (7, 40, 1, 33, 72, None, False),           # single image row
+    (2, 64, 33, 1, 96, ('relu',), False),         # single image column
+])
+def test_pool_fused_conv_bit_identical_to_separate_kernels_and_vs_oracle(shape):
+    from oracle import ref_ops
+    from pyopenvino_b200 import _cabi, kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    n, cin, h, w, cout, act, sliced = shape
+    rng = np.random.default_rng(abs(hash(shape[:5])) % (1 << 31))
+    # mixed signs: at the image border an all-negative window must produce 0 (the zero padding takes part in the max)
+    x = (rng.standard_normal((n, cin, h, w)) - 0.8).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, cout, 1, 1))).astype(np.float32)
+    if sliced:
+        wide = np.full((n, cin + 16, h, w), np.float32(1e9))
+        wide[:, 8:8 + cin] = x
+        xd = kernels.channel_slice(kernels.to_nhwc(kernels.upload(wide)), 8, cin)
+        out_f = kernels.channel_slice(kernels.new_nhwc(n, cout + 64, h, w), 32, cout)
+        out_s = kernels.channel_slice(kernels.new_nhwc(n, cout + 64, h, w), 32, cout)
+    else:
+        xd = kernels.to_nhwc(kernels.upload(x))
+        out_f = out_s = None
+    wd, bd = kernels.upload(wt), kernels.upload(b)
+    kernels.pack_conv(wd)
+    launches0 = _cabi.launch_count
+    fused = kernels.conv2d(xd, wd, (1, 1), (0, 0), (h, w), bias=bd, act=act, out=out_f, pre_pool=True)
+    assert _cabi.launch_count - launches0 == (1 if w <= 63 else 2), 'the fused pair must be ONE library call'
+    pooled = kernels.pool2d(xd, _cabi.POOL_MAX, (3, 3), (1, 1), (1, 1), (1, 1), (h, w))
+    separate = kernels.conv2d(pooled, wd, (1, 1), (0, 0), (h, w), bias=bd, act=act, out=out_s)
+    got, sep = np.asarray(fused), np.asarray(separate)
+    assert np.array_equal(got, sep), 'fused pool->conv differs from pool2d + conv2d (max |d| = {})'.format(np.abs(got - sep).max())
+    p = ref_ops.maxpool(POOL_DATA, x)
+    assert np.array_equal(np.asarray(pooled), p)
+    want = ref_ops.conv_special(p, wt, (1, 1), (0, 0), (0, 0), 'explicit') + b
+    if act == ('relu',):
+        want = np.maximum(want, 0)
+    elif act is not None:
+        want = np.clip(want, act[1], act[2])
+    ok, msg = close(got, want)
+    assert ok, msg
+
+
+def test_pool_fusion_falls_back_outside_the_f16x2_path():
+    """pre_pool with the FP32-range arithmetic (the range fallback's re-run) or FP16 storage: kernels.conv2d issues the
+    separate MaxPool; the C entry point itself refuses instead of silently dropping the pooling."""
+    import ctypes as C
+    from oracle import ref_ops
+    from pyopenvino_b200 import _cabi, kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((2, 32, 9, 9)) - 0.5).astype(np.float32)
+    wt = (rng.standard_normal((24, 32, 1, 1)) * 0.2).astype(np.float32)
+    xd, wd = kernels.to_nhwc(kernels.upload(x)), kernels.upload(wt)
+    want = ref_ops.conv_special(ref_ops.maxpool(POOL_DATA, x), wt, (1, 1), (0, 0), (0, 0), 'explicit')
+    for math in (_cabi.MATH_SAFE, _cabi.MATH_FP32, _cabi.MATH_TF32X3):
+        y = kernels.conv2d(xd, wd, (1, 1), (0, 0), (9, 9), math=math, pre_pool=True)
+        ok, msg = close(np.asarray(y), want)
+        assert ok, (math, msg)
+    pk = kernels.pack_conv(wd)
+    out = kernels.new_nhwc(2, 24, 9, 9)
+    d = _cabi.ConvDesc(n=2, h=9, w=9, cin=32, cout=24, kh=1, kw=1, sh=1, sw=1, pt=0, pl=0, oh=9, ow=9, x_ld=xd.ld, y_ld=out.ld,
+                       ldw=pk.ldw, act=0, act_lo=0.0, act_hi=0.0, math=_cabi.MATH_FP32, x_dtype=0, y_dtype=0,
+                       pre_pool=_cabi.PREPOOL_MAX3X3S1)
+    rc = _cabi.load().b200ov_conv2d(C.byref(d), C.c_void_p(xd.ptr), C.c_void_p(pk.ptr), None, C.c_void_p(out.ptr), None)
+    assert rc == _cabi.ERR_UNSUPPORTED
+
+
+def test_googlenet_pool_fusion_end_to_end(model_dir):
+    """The nine pool -> pool_proj pairs of GoogLeNet run fused (nine launches fewer per inference) and the network
+    output is bit-identical to the plan without the fusion (B200OV_NO_POOL_FUSE=1)."""
+    from pyopenvino_b200.inference_engine import IECore
+    from tools.synth_bin import synth_input
+    ie = IECore()
+    xml = os.path.join(model_dir, 'googlenet-v1.xml')
+    x = synth_input('googlenet-v1', batch=8, seed=3)
+    outs, launches = [], []
+    for off in ('0', '1'):
+        os.environ['B200OV_NO_POOL_FUSE'] = off
+        try:
+            net = ie.read_network(xml, xml[:-4] + '.bin')
+            exe = ie.load_network(net, 'B200', batch_size=8)
+            name, out_name = net.inputs[0]['name'], net.outputs[0]['name']
+            outs.append(exe.infer({name: x})[out_name])
+            outs.append(exe.infer({name: x})[out_name])          # graph replay
+            launches.append(exe.kernels_per_inference())
+            if off == '0':
+                assert sum(1 for s in exe._plan.values() if s.get('pool_into') is not None) == 9
+        finally:
+            os.environ.pop('B200OV_NO_POOL_FUSE', None)
+    assert launches[1] - launches[0] == 9, launches
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)

@@ -46,6 +46,17 @@ LAYERS = [
     ('G pool1 3x3s2', 'maxpool', dict(c=64, k=3, s=2, p=0, hw=112)),
     ('G 3a/pool 3x3s1', 'maxpool', dict(c=192, k=3, s=1, p=1, hw=28)),
     ('G 5a/pool 3x3s1', 'maxpool', dict(c=832, k=3, s=1, p=1, hw=7)),
+    # pool -> pool_proj pairs of the inception modules: fused (MaxPool inside the 1x1 convolution's A producers) / separate
+    ('G 3a/pool+proj fused', 'poolconv', dict(cin=192, cout=32, hw=28)),
+    ('G 3a/pool+proj sep', 'poolconv_sep', dict(cin=192, cout=32, hw=28)),
+    ('G 3b/pool+proj fused', 'poolconv', dict(cin=256, cout=64, hw=28)),
+    ('G 3b/pool+proj sep', 'poolconv_sep', dict(cin=256, cout=64, hw=28)),
+    ('G 4a/pool+proj fused', 'poolconv', dict(cin=480, cout=64, hw=14)),
+    ('G 4a/pool+proj sep', 'poolconv_sep', dict(cin=480, cout=64, hw=14)),
+    ('G 4e/pool+proj fused', 'poolconv', dict(cin=528, cout=128, hw=14)),
+    ('G 4e/pool+proj sep', 'poolconv_sep', dict(cin=528, cout=128, hw=14)),
+    ('G 5a/pool+proj fused', 'poolconv', dict(cin=832, cout=128, hw=7)),
+    ('G 5a/pool+proj sep', 'poolconv_sep', dict(cin=832, cout=128, hw=7)),
     ('G pool5 avg7', 'avgpool', dict(c=1024, k=7, s=1, p=0, hw=7)),
     ('G norm1 lrn', 'lrn', dict(c=64, hw=56)),
     ('G norm2 lrn', 'lrn', dict(c=192, hw=56)),
@@ -91,6 +102,18 @@ def main():
                 bias = kernels.upload(np.zeros((1, q['cout'], 1, 1), np.float32))
                 fused = {'bias': bias, 'act': ('relu',)}
                 typ = 'Convolution'
+            elif kind in ('poolconv', 'poolconv_sep'):
+                x = np.maximum(rng.standard_normal((B, q['cin'], q['hw'], q['hw'])), 0).astype(np.float32)
+                w = (rng.standard_normal((q['cout'], q['cin'], 1, 1)) * np.sqrt(2.0 / q['cin'])).astype(np.float32)
+                node = {'name': tag, 'type': 'Convolution', 'data': {'strides': '1, 1', 'dilations': '1, 1', 'pads_begin': '0, 0',
+                        'pads_end': '0, 0', 'auto_pad': 'explicit'}, 'input': {0: fp(x.shape), 1: fp(w.shape)}, 'output': {2: fp(())}}
+                pnode = {'name': tag + ' pool', 'type': 'MaxPool', 'data': {'strides': '1, 1', 'kernel': '3, 3', 'pads_begin': '1, 1',
+                         'pads_end': '1, 1', 'rounding_type': 'ceil', 'auto_pad': 'explicit'}, 'input': {0: fp(x.shape)}, 'output': {1: fp(())}}
+                ins = {0: kernels.to_nhwc(kernels.upload(x)), 1: kernels.upload(w)}
+                fused = {'bias': kernels.upload(np.zeros((1, q['cout'], 1, 1), np.float32)), 'act': ('relu',)}
+                if kind == 'poolconv':
+                    fused['pre_pool'] = 0
+                typ = 'Convolution'
             elif kind == 'dw':
                 x = rng.standard_normal((B, q['c'], q['hw'], q['hw'])).astype(np.float32)
                 w = rng.standard_normal((q['c'], 1, 1, 3, 3)).astype(np.float32)
@@ -126,6 +149,10 @@ def main():
                 typ = 'MatMul'
             call = (lambda: plugins[typ].compute(node, ins, kernel_type=args.math, fused=fused)) if fused is not None else \
                 (lambda: plugins[typ].compute(node, ins, kernel_type=args.math))
+            if kind == 'poolconv_sep':
+                def call(node=node, pnode=pnode, ins=ins, fused=fused):
+                    pooled = plugins['MaxPool'].compute(pnode, {0: ins[0]}, kernel_type=args.math)[1]
+                    return plugins['Convolution'].compute(node, {0: pooled, 1: ins[1]}, kernel_type=args.math, fused=fused)
             try:
                 y = next(iter(call().values()))
             except Exception as e:          # e.g. tcgen05 modes on C_in = 3 stems
@@ -135,6 +162,8 @@ def main():
             nbytes = 4 * (in_elems + y.size)
             if kind == 'conv':
                 flops = 2 * y.size * q['cin'] * q['k'] ** 2
+            elif kind in ('poolconv', 'poolconv_sep'):
+                flops = 2 * y.size * q['cin']
             elif kind == 'dw':
                 flops = 2 * y.size * 9
             elif kind == 'matmul':
