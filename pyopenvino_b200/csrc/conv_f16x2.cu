@@ -472,8 +472,12 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         for (int slot = 0; slot < p.num_slots; ++slot) {
           mbar_wait(bar_pool_empty(st), phase ^ 1);
           if (elect_one_sync()) {
+#ifdef B200OV_POOL_EXP_NOTMA
+            mbar_arrive(bar_pool_full(st));
+#else
             mbar_arrive_expect_tx(bar_pool_full(st), (uint32_t)p.pool_rows * 128u);
             tma_load_2d(base + L::POOL_RING + st * p.pool_stage_bytes, &map_x, slot * SLOT_K, r0, bar_pool_full(st));
+#endif
           }
           __syncwarp();
           if (++st == p.pool_stages) { st = 0; phase ^= 1; }
@@ -498,6 +502,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     int riy[4], rix[4];
     int prow[4], pflag[4];             // POOL: box row of the window centre; bits: 1 up, 2 down, 4 left, 8 right neighbour inside the image, 16 row < M
     uint32_t cur_tl = 0xffffffffu, cur_slot0 = 0;
+    uint32_t pool_release = 0;         // POOL: "stage consumed" barrier of the item between issue_loads and convert_store
     F16_TRACE_DECL
     auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
       uint32_t tl, slot;
@@ -511,7 +516,9 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         const int m0 = (int)m_blk_ * BLOCK_M;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int m = m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
+          // POOL: the thread's four rows are four CONSECUTIVE pixels (tile row 16g + 8h + rsub <-> pixel 4 rsub + 2g + h of the
+          // warp's 32), so their 3x3 windows share columns; the epilogue undoes the permutation when it stages the tile
+          const int m = POOL ? m0 + 32 * q + 4 * rsub + r : m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
           uint32_t img, rem, oy, ox;
           p.d_ohow.divmod((uint32_t)(m < p.M ? m : 0), img, rem);
           p.d_ow.divmod(rem, oy, ox);
@@ -535,35 +542,51 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         p.d_pool_stages.divmod(item, round, st);
         mbar_wait(bar_pool_full(st), round & 1);
         const uint32_t sbase = base + L::POOL_RING + st * p.pool_stage_bytes;
+        // The four windows cover 6 pixel columns (linear neighbours p - 1 .. p + 4 of the thread's first pixel p) x 3 image rows:
+        // 18 pixel positions instead of 36.  Column maxima first (vertical), then each output takes its three columns.  A
+        // vertical tap outside the image is aliased to the centre row; a horizontal neighbour that belongs to another image row
+        // (x = 0 / x = w - 1; the linear neighbour is then the previous / next row's pixel) is clamped to <= 0 with a min, which
+        // is exact because such a pixel takes the zero padding into its max anyway (MaxPool.py:41-72).  Rows past M sit beyond
+        // the tensor map's pixel dimension and read TMA's zero fill.
+        float4 cm[6][2];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int f = pflag[c == 0 ? 0 : (c == 5 ? 3 : c - 1)];
+          const int rowc = prow[0] + c - 1;
+          float4 t[3][2];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int row = rowc + (dy == 0 ? ((f & 1) ? -p.w : 0) : (dy == 1 ? 0 : ((f & 2) ? p.w : 0)));
+            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4) ^ (row & 7)) << 4);
+#ifdef B200OV_POOL_EXP_1TAP
+            if (dy != 1) { t[dy][0] = t[dy][1] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+#endif
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dy][0].x), "=f"(t[dy][0].y), "=f"(t[dy][0].z), "=f"(t[dy][0].w) : "r"(a));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dy][1].x), "=f"(t[dy][1].y), "=f"(t[dy][1].z), "=f"(t[dy][1].w) : "r"(a ^ 16u));
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            cm[c][hf].x = fmaxf(fmaxf(t[0][hf].x, t[1][hf].x), t[2][hf].x); cm[c][hf].y = fmaxf(fmaxf(t[0][hf].y, t[1][hf].y), t[2][hf].y);
+            cm[c][hf].z = fmaxf(fmaxf(t[0][hf].z, t[1][hf].z), t[2][hf].z); cm[c][hf].w = fmaxf(fmaxf(t[0][hf].w, t[1][hf].w), t[2][hf].w);
+          }
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int f = pflag[r];
-          const int oy0 = (f & 1) ? -p.w : 0, oy2 = (f & 2) ? p.w : 0, ox0 = (f & 4) ? -1 : 0, ox2 = (f & 8) ? 1 : 0;
-          const float edge = (f & 15) == 15 ? -INFINITY : 0.f;
-          float mx[8];
+          const float lim_l = (f & 4) ? INFINITY : 0.f, lim_r = (f & 8) ? INFINITY : 0.f, edge = (f & 15) == 15 ? -INFINITY : 0.f;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int rowy = prow[r] + (dy == 0 ? oy0 : (dy == 1 ? 0 : oy2));
-            float4 t[3][2];
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const int row = rowy + (dx == 0 ? ox0 : (dx == 1 ? 0 : ox2));
-              const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4) ^ (row & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dx][0].x), "=f"(t[dx][0].y), "=f"(t[dx][0].z), "=f"(t[dx][0].w) : "r"(a));
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[dx][1].x), "=f"(t[dx][1].y), "=f"(t[dx][1].z), "=f"(t[dx][1].w) : "r"(a ^ 16u));
-            }
-            float rowmax[8];
-            rowmax[0] = fmaxf(fmaxf(t[0][0].x, t[1][0].x), t[2][0].x); rowmax[1] = fmaxf(fmaxf(t[0][0].y, t[1][0].y), t[2][0].y);
-            rowmax[2] = fmaxf(fmaxf(t[0][0].z, t[1][0].z), t[2][0].z); rowmax[3] = fmaxf(fmaxf(t[0][0].w, t[1][0].w), t[2][0].w);
-            rowmax[4] = fmaxf(fmaxf(t[0][1].x, t[1][1].x), t[2][1].x); rowmax[5] = fmaxf(fmaxf(t[0][1].y, t[1][1].y), t[2][1].y);
-            rowmax[6] = fmaxf(fmaxf(t[0][1].z, t[1][1].z), t[2][1].z); rowmax[7] = fmaxf(fmaxf(t[0][1].w, t[1][1].w), t[2][1].w);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) mx[i] = dy == 0 ? fmaxf(rowmax[i], edge) : fmaxf(mx[i], rowmax[i]);
+          for (int hf = 0; hf < 2; ++hf) {
+#define B200OV_OUT(F_) fmaxf(fmaxf(fmaxf(fminf(cm[r][hf].F_, lim_l), cm[r + 1][hf].F_), fminf(cm[r + 2][hf].F_, lim_r)), edge)
+            dst[r].v[4 * hf + 0] = B200OV_OUT(x); dst[r].v[4 * hf + 1] = B200OV_OUT(y);
+            dst[r].v[4 * hf + 2] = B200OV_OUT(z); dst[r].v[4 * hf + 3] = B200OV_OUT(w);
+#undef B200OV_OUT
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[r].v[i] = (f & 16) ? mx[i] : 0.f;
         }
-        mbar_arrive(bar_pool_empty(st));                 // every value of the stage this thread needs is in its registers
+        // The stage is released in convert_store, after the tcgen05.st that consume every value loaded here: an arrive placed
+        // here is not ordered behind the LDS still queued in the (saturated) shared-memory pipe -- it overtook them and the
+        // loader's refill of the stage then raced the last loads of the window (seen as wrong fourth pixels of a group on the
+        // first item of a tile, when the loader is already waiting for the stage).
+        pool_release = bar_pool_empty(st);
       } else if constexpr (!PAIR) {
         uint32_t tap, cu, ky, kx;
         p.d_upt.divmod(unit, tap, cu);
@@ -638,6 +661,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         split_pair(r1.v[6], r1.v[7], v[7], v[15]);
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
+      if constexpr (POOL) mbar_arrive(pool_release);       // (after the stores: see issue_loads)
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
       __syncwarp();
@@ -647,6 +671,13 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     Run8 d0[4], d1[4];
     for (uint32_t item = 2 * set; item < total_items; item += 2 * NUM_SETS) {
       const bool two = item + 1 < total_items;
+      if constexpr (POOL) {
+        // shared-memory gather: nothing to overlap with a second item's loads, and one buffer leaves the registers to the window
+        issue_loads(item, d0);
+        convert_store(item, d0);
+        if (two) { issue_loads(item + 1, d0); convert_store(item + 1, d0); }
+        continue;
+      }
       F16_TIMED(1, issue_loads(item, d0); if (two) issue_loads(item + 1, d1));
       if (q == 0 && lane == 0) { F16_STAMP(0, item); F16_STAMP(0, item + 1); }
       F16_TIMED(3, convert_store(item, d0));
@@ -663,6 +694,8 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     const uint32_t stage_u32 = base + L::STAGING + q * L::STG_BLOCKS * 4096;
     uint8_t* stage_ptr = base_ptr + L::STAGING + q * L::STG_BLOCKS * 4096;
     uint32_t chunkcount = 0;
+    // staging row of this thread's accumulator lane: the pixel order (POOL: the producers' permutation undone, see there)
+    const int srow = POOL ? 4 * (lane & 7) + (lane >> 3) : lane;
     f32x2 chk = pack_f32x2(0.f, 0.f);
     const float act_lo = p.act == B200OV_ACT_NONE ? -INFINITY : (p.act == B200OV_ACT_RELU ? 0.f : p.lo);
     const float act_hi = p.act == B200OV_ACT_CLAMP ? p.hi : INFINITY;
@@ -787,7 +820,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
             float4 o;
             o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
             o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
-            *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
+            *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + srow * 128 + ((c4 ^ (srow & 7)) << 4)) = o;
           }
         }
         if (p.tma_store) {
