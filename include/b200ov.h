@@ -66,9 +66,12 @@ enum {
  * rounds to nearest even on store, halving the bytes of the bandwidth-bound layers.  The reference's plugins are
  * dtype-generic (common_def.py:18-19) and its original IRs were FP16 (GroupConvolution.py:136-143). */
 enum { B200OV_DT_F32 = 0, B200OV_DT_F16 = 1, B200OV_DT_U8 = 2, B200OV_DT_I8 = 3,
-       B200OV_DT_HL = 4   /* network input pre-split for the stem contraction: per pixel (<= 4 channels, 16 bytes)
-                             [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] FP16 pairs with c = hi + 2^-11 lo -- the same
-                             22 significant bits the contraction's own split keeps; only b200ov_conv2d reads it */
+       B200OV_DT_HL = 4   /* the contraction's own operand form, same 4 bytes per value as FP32: per 4 channels (16 bytes)
+                             [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] FP16 pairs with c = hi + 2^-11 lo -- exactly the 22
+                             significant bits the contraction's split keeps, so a contraction reading it produces the same
+                             bits as on the FP32 tensor.  Written by b200ov_input_to_nhwc_split (network input of a <= 4
+                             channel stem) and by b200ov_conv2d / _multi / b200ov_dwconv2d for outputs whose only readers
+                             are contractions (y_dtype); only b200ov_conv2d / _multi read it */
 };
 
 /* ---- library / device -------------------------------------------------------------------- */
@@ -144,6 +147,8 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const void* x, const float* w_packe
 typedef struct {
   void* y;
   int32_t col0, cout, y_ld;
+  int32_t y_dtype;             /* B200OV_DT_F32 (0: the descriptor's y_dtype) or B200OV_DT_HL: this output is read by
+                                  contractions only (cout % 4 == 0, 16-byte aligned pixels)                       */
 } b200ov_conv_seg;
 int b200ov_conv2d_multi(const b200ov_conv_desc* d, const void* x, const float* w_packed, const float* bias,
                         int nseg, const b200ov_conv_seg* segs, void* stream);

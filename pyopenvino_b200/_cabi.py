@@ -40,7 +40,7 @@ DW_AUTO, DW_EXACT = 0, 1
 
 
 class ConvSeg(C.Structure):
-    _fields_ = [('y', C.c_void_p), ('col0', C.c_int32), ('cout', C.c_int32), ('y_ld', C.c_int32)]
+    _fields_ = [('y', C.c_void_p), ('col0', C.c_int32), ('cout', C.c_int32), ('y_ld', C.c_int32), ('y_dtype', C.c_int32)]
 
 
 class PoolDesc(C.Structure):

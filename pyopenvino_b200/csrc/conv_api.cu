@@ -68,7 +68,7 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const void* x_raw, const float* w_p
   if (d->x_dtype != B200OV_DT_F32 || d->y_dtype != B200OV_DT_F32) {
     // FP16 feature maps: only the f16x2 contraction reads / writes them
     B200OV_REQUIRE((d->x_dtype == B200OV_DT_F32 || d->x_dtype == B200OV_DT_F16 || d->x_dtype == B200OV_DT_HL) &&
-                       (d->y_dtype == B200OV_DT_F32 || d->y_dtype == B200OV_DT_F16),
+                       (d->y_dtype == B200OV_DT_F32 || d->y_dtype == B200OV_DT_F16 || d->y_dtype == B200OV_DT_HL),
                    "conv2d: bad storage type");
     if ((d->math != B200OV_MATH_AUTO && d->math != B200OV_MATH_F16X2) || !f16x2_eligible(d, x_raw))
       return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: FP16 feature maps need the f16x2 path (cin %% 8 == 0, 16-byte aligned pixels)");

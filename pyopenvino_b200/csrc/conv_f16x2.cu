@@ -99,6 +99,7 @@ struct Params {
   // output segments: fused columns [seg_col0, seg_col0 + seg_cout) go to tensor seg_y (pitch seg_yld); seg_col0 is a
   // multiple of 32.  One segment for an ordinary convolution, up to three for sibling 1x1 convolutions run as one GEMM.
   int nseg;
+  int seg_hl;                          // bit i: segment i is written as FP16 (hi, scaled lo) pairs (B200OV_DT_HL) for a contraction to read
   int seg_col0[3], seg_cout[3], seg_yld[3];
   float* seg_y[3];
   int prefetch;                        // 1: L2 prefetch of the set's next slot pair (long channel runs, HBM-bound layers)
@@ -811,6 +812,12 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
 #pragma unroll
         for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
           const int qb = round * L::STG_BLOCKS + sb;
+          // A segment another contraction reads is written in that kernel's operand form: per 4 channels (16 bytes)
+          // [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] -- exactly what its producers would compute from the FP32 values, once
+          // per element here instead of once per filter tap and column tile there.
+          int local_hl = 0;
+          const int sg_hl = p.seg_hl != 0 ? segment_of(n0 + qb * 32, local_hl) : -1;
+          const bool as_hl = sg_hl >= 0 && ((p.seg_hl >> sg_hl) & 1);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const f32x2 a0 = acc[qb * 16 + c4 * 2], a1 = acc[qb * 16 + c4 * 2 + 1];
@@ -820,6 +827,12 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
             float4 o;
             o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
             o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
+            if (as_hl) {
+              uint32_t h01, l01, h23, l23;
+              split_pair(o.x, o.y, h01, l01);
+              split_pair(o.z, o.w, h23, l23);
+              o = make_float4(__uint_as_float(h01), __uint_as_float(h23), __uint_as_float(l01), __uint_as_float(l23));
+            }
             *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + srow * 128 + ((c4 ^ (srow & 7)) << 4)) = o;
           }
         }
@@ -1005,9 +1018,12 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
 // pixel pitch of exactly 4 floats (a run = two adjacent taps; the producer of x zero-fills the pad lanes, e.g. the
 // network-input layout kernel writes a 3-channel image with pitch 4).
 bool f16x2_eligible(const b200ov_conv_desc* d, const void* x) {
-  if (d->x_dtype == B200OV_DT_HL)      // pre-split network input: the stem's 8-channel super-pixel view only
-    return d->cin <= 4 && d->x_ld == 4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0 &&
-           d->act != B200OV_ACT_SIGMOID;
+  if (d->x_dtype == B200OV_DT_HL) {
+    if (d->cin <= 4)                   // pre-split network input: the stem's 8-channel super-pixel view only
+      return d->x_ld == 4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0 && d->act != B200OV_ACT_SIGMOID;
+    // a feature map another contraction's epilogue wrote as (hi, lo) pairs, 16 bytes per 4 channels
+    return (d->x_ld % 4 == 0) && aligned16(x) && d->cin % 8 == 0 && d->act != B200OV_ACT_SIGMOID;
+  }
   if (d->x_dtype == B200OV_DT_F16)     // FP16 feature map in: 8-channel runs of 16 bytes
     return (d->x_ld % 8 == 0) && aligned16(x) && d->cin % 8 == 0 && d->act != B200OV_ACT_SIGMOID;
   return (d->x_ld % 4 == 0) && aligned16(x) && (d->cin % 8 == 0 || (d->cin <= 4 && d->x_ld == 4)) &&
@@ -1076,6 +1092,13 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
         segs[i].y_ld < segs[i].cout)
       return set_error(B200OV_ERR_INVALID, "conv2d: bad output segment %d", i);
     p.seg_col0[i] = segs[i].col0; p.seg_cout[i] = segs[i].cout; p.seg_yld[i] = segs[i].y_ld; p.seg_y[i] = static_cast<float*>(segs[i].y);
+    if (segs[i].y_dtype == B200OV_DT_HL) {
+      if (o16 || segs[i].cout % 4 != 0 || segs[i].y_ld % 4 != 0 || !aligned16(segs[i].y))
+        return set_error(B200OV_ERR_INVALID, "conv2d: an (hi, lo)-pair output needs whole 16-byte channel groups (segment %d)", i);
+      p.seg_hl |= 1 << i;
+    } else if (segs[i].y_dtype != B200OV_DT_F32 && segs[i].y_dtype != d->y_dtype) {
+      return set_error(B200OV_ERR_INVALID, "conv2d: bad storage type of output segment %d", i);
+    }
     if (segs[i].y_ld % (o16 ? 8 : 4) != 0 || !aligned16(segs[i].y)) p.tma_store = 0;     // (FP16 out: "vector stores allowed")
   }
   int coutp, kpad, upt, units;
@@ -1084,7 +1107,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   p.num_slots = ceil_div(units, 4);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > 1) {
-    if (nseg != 1 || bias != nullptr || d->act != B200OV_ACT_NONE || ws_rows < (int)M || o16)
+    if (nseg != 1 || bias != nullptr || d->act != B200OV_ACT_NONE || ws_rows < (int)M || o16 || p.seg_hl != 0)
       return set_error(B200OV_ERR_INVALID, "conv2d: split-K writes raw partial sums of one tensor (no bias / activation)");
     p.num_slots = round_up(ceil_div(p.num_slots, ksplit), 2);     // whole weight stages; the last split's tail reads zeros
   }
@@ -1181,7 +1204,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
 
 int conv2d_f16x2(const b200ov_conv_desc* d, const void* x, const float* wt, const float* bias, void* y, cudaStream_t s) {
   b200ov_conv_seg seg;
-  seg.y = y; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = d->y_ld;
+  seg.y = y; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = d->y_ld; seg.y_dtype = d->y_dtype == B200OV_DT_HL ? B200OV_DT_HL : B200OV_DT_F32;
   return conv2d_f16x2_multi(d, x, wt, bias, 1, &seg, s, 1, 0);
 }
 
@@ -1222,7 +1245,7 @@ int conv2d_f16x2_splitk(const b200ov_conv_desc* d, const void* x, const float* w
   b200ov_conv_desc dd = *d;
   dd.act = B200OV_ACT_NONE;
   b200ov_conv_seg seg;
-  seg.y = ws; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = ws_ld;
+  seg.y = ws; seg.col0 = 0; seg.cout = d->cout; seg.y_ld = ws_ld; seg.y_dtype = B200OV_DT_F32;
   int rc = conv2d_f16x2_multi(&dd, x, wt, nullptr, 1, &seg, s, ksplit, ws_rows);
   if (rc) return rc;
   const bool vec = d->cout % 4 == 0 && d->y_ld % 4 == 0 && aligned16(y) && (bias == nullptr || aligned16(bias));

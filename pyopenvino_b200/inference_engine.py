@@ -529,6 +529,29 @@ class Executable_Network:
                 if G.nodes[head]['type'] in ('ReLU', 'Clamp', 'Sigmoid', 'LRN') and head != tail_id:
                     continue
                 plan[head]['out_slot'] = (n, coff, c)
+        # Contraction -> contraction edges (3x3_reduce -> 3x3, 5x5_reduce -> 5x5, the 1x1 -> 3x3/s2 pairs of the SSD extra
+        # layers): the producer's epilogue leaves the tensor in the consumer's operand form (FP16 hi / scaled-lo pairs, the same
+        # 4 bytes per value), so the consumer's A producers only route words instead of splitting every value once per filter
+        # tap and column tile.  Same bits downstream; FP32 storage only; never for a tensor anything else reads.
+        if self.storage == 'f32' and os.environ.get('B200OV_NO_HL') != '1':
+            for n in self.task_list:
+                node = G.nodes[n]
+                if node['type'] != 'Convolution' or plan[n]['skip'] or plan[n]['out_slot'] is not None or 'output' not in node:
+                    continue
+                tail = plan[n]['store_as']
+                cout = node['output'][common_def.first_output_port(node)]['dims'][1]
+                readers = list(G.successors(tail))
+                if cout % 8 != 0 or not readers:
+                    continue
+                ok = True
+                for r in readers:
+                    rn = G.nodes[r]
+                    if rn['type'] != 'Convolution' or plan[r]['skip'] or G.edges[(tail, r)]['connection'][3] != 0 or \
+                            'pre_pool' in plan[r]['ops'] or common_def.string_to_tuple(rn['data']['dilations']) != (1, 1):
+                        ok = False
+                        break
+                if ok:
+                    plan[n]['ops']['hl_out'] = True
         # Sibling 1x1 convolutions (same input, stride 1, no padding, bias + the same activation): one contraction
         # with several output tensors -- the 1x1 / 3x3_reduce / 5x5_reduce branches of an inception module read
         # (and FP16-split) their common input once instead of three times.
@@ -622,6 +645,8 @@ class Executable_Network:
                         # eager fused mode: a Parameter scheduled ahead of the Const it folded (`data/mean`) -- evaluate it now
                         cnode['output'][0]['data'] = p.plugins['Const'].compute(cnode, {}, kernel_type=self.kernel_type, debug=False)[0]
                     fused[key] = cnode['output'][0]['data']
+                elif key == 'hl_out' and (self.expected_result is not None or self.pickle_node_args or verbose):
+                    continue                     # debug modes read every node output on the host: keep it FP32
                 else:
                     fused[key] = val
             if step['out_slot'] is not None:
@@ -717,7 +742,7 @@ class Executable_Network:
                     n_, c_, h_, w_ = G.nodes[cid]['output'][common_def.first_output_port(G.nodes[cid])]['dims']
                     concat_bufs[cid] = kernels.new_nhwc(n_, c_, h_, w_)
                 out = kernels.channel_slice(concat_bufs[cid], coff, c)
-            specs.append((ins[1], bias, out))
+            specs.append((ins[1], bias, out, bool(st['ops'].get('hl_out')) and out is None))
         ev = None
         if self._step_events is not None:
             import torch

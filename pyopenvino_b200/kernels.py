@@ -29,6 +29,8 @@ def as_f32(x):
     FP16-storage variant."""
     if x.layout != 'nhwc' or x.st == 'f32':
         return x
+    if x.st == 'hl':
+        raise _cabi.B200ovError('an (hi, lo)-pair feature map can only be read by a contraction (planner error)')
     n, c, h, w = x.shape
     out = new_nhwc(n, c, h, w, st='f32')
     _cabi.call('b200ov_copy2d_st', _p(x), x.code, _p(out), out.code, x.pixels, c, x.ld, out.ld, _s())
@@ -194,7 +196,7 @@ def as_plain(x):
 def new_nhwc(n, c, h, w, st=None):
     st = pick_st(c) if st is None else st
     elems = n * h * w * c
-    return DeviceArray(dev.alloc_f32(elems if st == 'f32' else (elems + 1) // 2), (n, c, h, w), 'nhwc', ld=c, st=st)
+    return DeviceArray(dev.alloc_f32((elems + 1) // 2 if st == 'f16' else elems), (n, c, h, w), 'nhwc', ld=c, st=st)
 
 
 def _check_out(out, shape):
@@ -271,8 +273,10 @@ def f16x2_ok(x, cin, act_code, mode):
     return x.ld % 4 == 0 and (cin % 8 == 0 or (cin <= 4 and x.ld == 4))
 
 
-def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None, pre_pool=False):
-    """`pre_pool`: x is the INPUT of a MaxPool 3x3 / stride 1 / pads 1 node whose only consumer is this 1x1 convolution; the
+def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, math=None, pre_pool=False, hl_out=False):
+    """`hl_out`: every reader of the result is a contraction -- where the f16x2 kernel takes this layer it writes the (hi, lo)
+    pair form those readers would otherwise compute per filter tap (DeviceArray.st == 'hl'; same bits downstream).
+    `pre_pool`: x is the INPUT of a MaxPool 3x3 / stride 1 / pads 1 node whose only consumer is this 1x1 convolution; the
     pooling runs inside the contraction's A producers (b200ov_conv_desc.pre_pool) where the f16x2 kernel takes the layer,
     as a separate b200ov_pool2d otherwise (FP32-range re-run, FP16 storage, unaligned slices)."""
     x = as_nhwc(x)
@@ -299,7 +303,10 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
     if final is not None and (final.st == 'f32' or half_ok):
         out = final
     else:
-        out = new_nhwc(*shape, st=pick_st(pk.cout) if half_ok else 'f32')
+        st = pick_st(pk.cout) if half_ok else 'f32'
+        if hl_out and half_ok and st == 'f32' and final is None and pk.cout % 8 == 0:
+            st = 'hl'
+        out = new_nhwc(*shape, st=st)
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=pk.cout, kh=pk.kh, kw=pk.kw, sh=strides[0], sw=strides[1],
                        pt=pads_begin[0], pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, ldw=pk.ldw,
                        act=code, act_lo=lo, act_hi=hi, math=mode, x_dtype=x.code, y_dtype=out.code,
@@ -316,6 +323,8 @@ def conv1x1_group(x, members, act=None):
     multiple of 32 columns) is built and packed once and cached on the first member's weight."""
     x = as_nhwc(x)
     n, c, h, wd = x.shape
+    hl_flags = [bool(m[3]) if len(m) > 3 else False for m in members]
+    members = [tuple(m[:3]) for m in members]
     ws = [as_device(m[0]) for m in members]
     key = ('group',) + tuple(id(w.t) for w in ws)
     cache = ws[0].cache
@@ -346,16 +355,21 @@ def conv1x1_group(x, members, act=None):
     for i, (w, (_, _b, o)) in enumerate(zip(ws, members)):
         shape = (n, w.shape[0], h, wd)
         final = _check_out(o, shape) if o is not None else None
-        o = final if final is not None and final.st == group_st else new_nhwc(*shape, st=group_st)
+        if final is None and hl_flags[i] and group_st == 'f32' and w.shape[0] % 8 == 0:
+            o = new_nhwc(*shape, st='hl')               # read by contractions only: written in their operand form
+        else:
+            o = final if final is not None and final.st == group_st else new_nhwc(*shape, st=group_st)
         finals.append(final)
         outs.append(o)
         segs[i].y = o.ptr
         segs[i].col0, segs[i].cout, segs[i].y_ld = col0s[i], w.shape[0], o.ld
+        segs[i].y_dtype = _cabi.DT_HL if o.st == 'hl' else _cabi.DT_F32
     code, lo, hi = _act(act)
-    st = outs[0].st
-    assert all(o.st == st for o in outs), 'grouped convolution outputs must share one storage type'
+    st = group_st
+    assert all(o.st in (st, 'hl') for o in outs), 'grouped convolution outputs must share one storage type'
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=total, kh=1, kw=1, sh=1, sw=1, pt=0, pl=0, oh=h, ow=wd, x_ld=x.ld, y_ld=total,
-                       ldw=pk.ldw, act=code, act_lo=lo, act_hi=hi, math=_cabi.MATH_AUTO, x_dtype=x.code, y_dtype=outs[0].code)
+                       ldw=pk.ldw, act=code, act_lo=lo, act_hi=hi, math=_cabi.MATH_AUTO, x_dtype=x.code,
+                       y_dtype=_cabi.DT_F16 if group_st == 'f16' else _cabi.DT_F32)
     _cabi.call('b200ov_conv2d_multi', C.byref(d), _p(x), C.c_void_p(pk.ptr), _p(fb), len(members), segs, _s())
     return [_into(o, f) for o, f in zip(outs, finals)]
 

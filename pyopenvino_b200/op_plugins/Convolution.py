@@ -6,7 +6,8 @@ strings parsed on every call, output size from the explicit / valid / same_* rul
 output port precision.  The arithmetic runs on the GPU as an implicit GEMM over NHWC feature maps
 (libb200ov `b200ov_conv2d`); an Add bias and a ReLU / Clamp that follow the node can be folded into
 the kernel epilogue through `fused`; `fused['pre_pool']` says that `inputs[0]` is the input of a 3x3 / stride-1
-MaxPool node (`MaxPool.py:41-72`) that the executor folded into this 1x1 convolution.
+MaxPool node (`MaxPool.py:41-72`) that the executor folded into this 1x1 convolution; `fused['hl_out']` that every reader
+of the result is a contraction (the result may then be left in that kernel's (hi, lo) operand form).
 """
 from .. import common_def, kernels, plugin_util
 
@@ -36,4 +37,4 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
     f = fused or {}
     return plugin_util.run_contraction(node, inputs, kernel_type, lambda math: kernels.conv2d(
         x, w, strides, pads_begin, out_hw, bias=f.get('bias'), act=f.get('act'), out=f.get('out'), math=math,
-        pre_pool=f.get('pre_pool') is not None))
+        pre_pool=f.get('pre_pool') is not None, hl_out=bool(f.get('hl_out'))))

@@ -116,3 +116,94 @@ def test_googlenet_pool_fusion_end_to_end(model_dir):
     assert launches[1] - launches[0] == 9, launches
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
+
+
+@pytest.mark.parametrize('shape', [
+    # n, cin, hw, cmid, cout, k, stride, pad
+    (2, 192, 28, 96, 128, 3, 1, 1),        # inception_3a 3x3_reduce -> 3x3
+    (3, 480, 14, 16, 48, 5, 1, 2),         # inception_4a 5x5_reduce -> 5x5
+    (2, 64, 19, 128, 256, 3, 2, 1),        # SSD extra layer: 1x1 -> 3x3 / stride 2
+    (1, 40, 9, 24, 20, 3, 1, 1),           # cmid = 24: K tail inside a slot, odd map
+])
+def test_hl_edge_between_contractions_is_bit_identical_and_vs_oracle(shape):
+    """A 1x1 convolution whose only reader is another convolution leaves its output as FP16 (hi, lo) pairs
+    (B200OV_DT_HL); the reader must produce exactly the bits it produces from the FP32 tensor."""
+    from oracle import ref_ops
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    n, cin, hw, cmid, cout, k, s, pad = shape
+    rng = np.random.default_rng(cin * 131 + cout)
+    x = np.maximum(rng.standard_normal((n, cin, hw, hw)), 0).astype(np.float32)
+    w1 = (rng.standard_normal((cmid, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal((1, cmid, 1, 1))).astype(np.float32)
+    w2 = (rng.standard_normal((cout, cmid, k, k)) * np.sqrt(2.0 / (cmid * k * k))).astype(np.float32)
+    b2 = (0.1 * rng.standard_normal((1, cout, 1, 1))).astype(np.float32)
+    xd = kernels.to_nhwc(kernels.upload(x))
+    w1d, b1d, w2d, b2d = (kernels.upload(a) for a in (w1, b1, w2, b2))
+    oh = (hw + 2 * pad - k) // s + 1
+    outs = []
+    for hl in (True, False):
+        mid = kernels.conv2d(xd, w1d, (1, 1), (0, 0), (hw, hw), bias=b1d, act=('relu',), hl_out=hl)
+        assert mid.st == ('hl' if hl else 'f32')
+        y = kernels.conv2d(mid, w2d, (s, s), (pad, pad), (oh, oh), bias=b2d, act=('relu',))
+        assert y.st == 'f32'
+        outs.append((np.asarray(mid), np.asarray(y)))
+    assert np.array_equal(outs[0][1], outs[1][1]), 'reader of the (hi, lo) tensor differs from the reader of the FP32 tensor'
+    # the debug decode of the pair form carries 22 significant bits of the FP32 values
+    assert np.allclose(outs[0][0], outs[1][0], rtol=3e-7, atol=1e-30)
+    mid_ref = np.maximum(ref_ops.conv_special(x, w1, (1, 1), (0, 0), (0, 0), 'explicit') + b1, 0)
+    want = np.maximum(ref_ops.conv_special(mid_ref, w2, (s, s), (pad, pad), (pad, pad), 'explicit') + b2, 0)
+    ok, msg = close(outs[0][1], want)
+    assert ok, msg
+
+
+def test_hl_group_segments(model_dir):
+    """b200ov_conv2d_multi with mixed FP32 / (hi, lo) output segments (the 1x1 | 3x3_reduce | 5x5_reduce contraction of an
+    inception module): the FP32 segment and the readers of the pair segments are bit-identical to the all-FP32 run."""
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(77)
+    n, cin, hw = 2, 256, 14
+    couts = (128, 96, 32)
+    x = np.maximum(rng.standard_normal((n, cin, hw, hw)), 0).astype(np.float32)
+    ws = [kernels.upload((rng.standard_normal((co, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float32)) for co in couts]
+    bs = [kernels.upload((0.05 * rng.standard_normal((1, co, 1, 1))).astype(np.float32)) for co in couts]
+    w3 = kernels.upload((rng.standard_normal((64, 96, 3, 3)) * 0.05).astype(np.float32))
+    w5 = kernels.upload((rng.standard_normal((48, 32, 5, 5)) * 0.05).astype(np.float32))
+    xd = kernels.to_nhwc(kernels.upload(x))
+    res = []
+    for hl in (True, False):
+        outs = kernels.conv1x1_group(xd, [(ws[0], bs[0], None, False), (ws[1], bs[1], None, hl), (ws[2], bs[2], None, hl)], act=('relu',))
+        assert [o.st for o in outs] == (['f32', 'hl', 'hl'] if hl else ['f32'] * 3)
+        y3 = kernels.conv2d(outs[1], w3, (1, 1), (1, 1), (hw, hw))
+        y5 = kernels.conv2d(outs[2], w5, (1, 1), (2, 2), (hw, hw))
+        res.append([np.asarray(outs[0]), np.asarray(y3), np.asarray(y5)])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('model,batch', [('googlenet-v1', 8), ('ssd_mobilenet_v1_coco', 2)])
+def test_models_with_hl_edges_bit_identical(model_dir, model, batch):
+    """Whole networks: the plan with contraction -> contraction tensors in (hi, lo) form against B200OV_NO_HL=1."""
+    from pyopenvino_b200.inference_engine import IECore
+    from tools.synth_bin import synth_input
+    ie = IECore()
+    xml = os.path.join(model_dir, model + '.xml')
+    x = synth_input(model, batch=batch, seed=5)
+    outs, edges = [], []
+    for off in ('0', '1'):
+        os.environ['B200OV_NO_HL'] = off
+        try:
+            net = ie.read_network(xml, xml[:-4] + '.bin')
+            exe = ie.load_network(net, 'B200', batch_size=batch)
+            name, out_name = net.inputs[0]['name'], net.outputs[0]['name']
+            outs.append(exe.infer({name: x})[out_name])
+            outs.append(exe.infer({name: x})[out_name])
+            edges.append(sum(1 for s in exe._plan.values() if s['ops'].get('hl_out')))
+        finally:
+            os.environ.pop('B200OV_NO_HL', None)
+    assert edges[0] > 0 and edges[1] == 0, edges
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
