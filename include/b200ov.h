@@ -189,6 +189,9 @@ typedef struct {
   float act_lo, act_hi;
   int32_t math;                /* B200OV_DW_*                                                    */
   int32_t dtype;               /* storage type of x and y: B200OV_DT_F32 (0, default) or B200OV_DT_F16 (3x3 only) */
+  int32_t y_dtype;             /* 0 / dtype: y stored like x.  B200OV_DT_HL (x FP32): y is read by contractions only (the
+                                  pointwise convolution after a depthwise one) and is written in their (hi, lo) operand
+                                  form; B200OV_ERR_UNSUPPORTED when the shape has no kernel for it (retry with 0)   */
 } b200ov_dwconv_desc;
 
 enum {

@@ -17,7 +17,7 @@ DT_F32, DT_F16, DT_U8, DT_I8, DT_HL = 0, 1, 2, 3, 4
 
 
 class B200ovError(RuntimeError):
-    pass
+    code = None               # the library's status code when the error came from an entry point
 
 
 class ConvDesc(C.Structure):
@@ -33,7 +33,8 @@ PREPOOL_NONE, PREPOOL_MAX3X3S1 = 0, 1
 class DwConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n', 'h', 'w', 'c', 'kh', 'kw', 'sh', 'sw', 'pt', 'pl', 'oh', 'ow',
                                          'x_ld', 'y_ld', 'act')] + [('act_lo', C.c_float), ('act_hi', C.c_float),
-                                                                    ('math', C.c_int32), ('dtype', C.c_int32)]
+                                                                    ('math', C.c_int32), ('dtype', C.c_int32),
+                                                                    ('y_dtype', C.c_int32)]
 
 
 DW_AUTO, DW_EXACT = 0, 1
@@ -143,7 +144,9 @@ def call(name, *args):
     global launch_count
     rc = getattr(load(), name)(*args)
     if rc != OK:
-        raise B200ovError('{} failed (code {}): {}'.format(name, rc, last_error()))
+        err = B200ovError('{} failed (code {}): {}'.format(name, rc, last_error()))
+        err.code = rc
+        raise err
     if name in _LAUNCHING:
         launch_count += 1
     return rc

@@ -44,6 +44,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f16split.cuh"
 #include "fastdiv.cuh"
 #include "tc_ptx.cuh"
 
@@ -215,19 +216,7 @@ __device__ __forceinline__ void split_pair(float c0, float c1, uint32_t& hi, uin
   hi = __float_as_uint(c0); lo = __float_as_uint(c1);
   return;
 #endif
-  const __half2 h = __floats2half2_rn(c0, c1);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float2 s = unpack_f32x2(mul2(pack_f32x2(c0, c1), pack_f32x2(LO_SCALE, LO_SCALE)));
-  float r0, r1;
-  asm("{\n\t.reg .b16 h0, h1, m;\n\t"
-      "mov.b32 {h0, h1}, %2;\n\t"
-      "mov.b16 m, 0xE800;\n\t"                       // -2048 as an FP16 number
-      "fma.rn.f32.f16 %0, h0, m, %3;\n\t"
-      "fma.rn.f32.f16 %1, h1, m, %4;\n\t}"
-      : "=f"(r0), "=f"(r1)
-      : "r"(hi), "f"(s.x), "f"(s.y));
-  const __half2 l = __floats2half2_rn(r0, r1);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  split_pair_f16x2(c0, c1, hi, lo);                  // f16split.cuh (shared with the kernels that WRITE the pair form)
 }
 
 struct Run8 {
@@ -827,12 +816,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
             float4 o;
             o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
             o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
-            if (as_hl) {
-              uint32_t h01, l01, h23, l23;
-              split_pair(o.x, o.y, h01, l01);
-              split_pair(o.z, o.w, h23, l23);
-              o = make_float4(__uint_as_float(h01), __uint_as_float(h23), __uint_as_float(l01), __uint_as_float(l23));
-            }
+            if (as_hl) o = encode_hl4(o.x, o.y, o.z, o.w);
             *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + srow * 128 + ((c4 ^ (srow & 7)) << 4)) = o;
           }
         }

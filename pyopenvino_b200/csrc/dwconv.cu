@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f16split.cuh"
 #include "fastdiv.cuh"
 #include "tc_ptx.cuh"
 #include "tma_util.cuh"
@@ -191,6 +192,7 @@ struct DwTmaP {
   int tw, tr, nimg, bw, bh;
   int stage_bytes, box_bytes;
   float lo, hi;
+  int y_hl;                            // 1: y is written as FP16 (hi, lo) pairs, 16 bytes per 4 channels (B200OV_DT_HL; T = float only)
   uint32_t items;
   FastDiv d_cchunks, d_coltiles, d_rowtiles, d_tw;
 };
@@ -324,8 +326,12 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
                 hi = fma2(R[(b0 + ky) % 3][kx].y, wt[ky * 3 + kx].y, hi);
               }
             const float2 a = unpack2(lo), b = unpack2(hi);
-            IO::st(yp, make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
-                                   act_t<ACT>(b.y, p.lo, p.hi)));
+            float4 o = make_float4(act_t<ACT>(a.x, p.lo, p.hi), act_t<ACT>(a.y, p.lo, p.hi), act_t<ACT>(b.x, p.lo, p.hi),
+                                   act_t<ACT>(b.y, p.lo, p.hi));
+            if constexpr (sizeof(T) == 4) {
+              if (p.y_hl) o = encode_hl4(o.x, o.y, o.z, o.w);      // the pointwise contraction's operand form (same 16 bytes)
+            }
+            IO::st(yp, o);
             yp += yrow;
           }
         }
@@ -348,6 +354,7 @@ static bool dw_tma_plan(const b200ov_dwconv_desc* d, DwTmaP& q, int esize) {
   q.items = (uint32_t)items;
   q.n = d->n; q.c = d->c; q.oh = d->oh; q.ow = d->ow; q.y_ld = d->y_ld; q.pt = d->pt; q.pl = d->pl;
   q.lo = d->act_lo; q.hi = d->act_hi;
+  q.y_hl = d->y_dtype == B200OV_DT_HL ? 1 : 0;
   q.d_cchunks = FastDiv(cchunks); q.d_coltiles = FastDiv(t.col_tiles); q.d_rowtiles = FastDiv(t.row_tiles); q.d_tw = FastDiv(q.tw);
   return true;
 }
@@ -496,6 +503,9 @@ int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const void* x_raw, const float*
   const int V = vec ? 4 : 1;
   const int cg = d->c / V;
   B200OV_REQUIRE(d->dtype == B200OV_DT_F32 || d->dtype == B200OV_DT_F16, "dwconv2d: bad storage type");
+  B200OV_REQUIRE(d->y_dtype == 0 || d->y_dtype == d->dtype || (d->y_dtype == B200OV_DT_HL && d->dtype == B200OV_DT_F32),
+                 "dwconv2d: bad output storage type");
+  const bool want_hl = d->y_dtype == B200OV_DT_HL;
   if (d->dtype == B200OV_DT_F16) {
     // FP16 feature maps: the TMA tile kernel only (3x3, stride 1 / 2, packed-FMA arithmetic)
     const bool ok = d->c % 4 == 0 && d->x_ld % 8 == 0 && d->y_ld % 4 == 0 && aligned16(x_raw) && aligned_vec4<__half>(y_raw) &&
@@ -538,6 +548,8 @@ int b200ov_dwconv2d(const b200ov_dwconv_desc* d, const void* x_raw, const float*
 #undef B200OV_DWT
     }
   }
+  // only the tile kernel above writes the (hi, lo) pair form: the caller falls back to an FP32 output
+  if (want_hl) return set_error(B200OV_ERR_UNSUPPORTED, "dwconv2d: this shape has no kernel that writes (hi, lo) pairs");
   if (hot) {
     DwStripP q;
     q.h = d->h; q.w = d->w; q.c = d->c; q.pt = d->pt; q.pl = d->pl; q.oh = d->oh; q.ow = d->ow; q.x_ld = d->x_ld;

@@ -536,7 +536,8 @@ class Executable_Network:
         if self.storage == 'f32' and os.environ.get('B200OV_NO_HL') != '1':
             for n in self.task_list:
                 node = G.nodes[n]
-                if node['type'] != 'Convolution' or plan[n]['skip'] or plan[n]['out_slot'] is not None or 'output' not in node:
+                if node['type'] not in ('Convolution', 'GroupConvolution') or plan[n]['skip'] or plan[n]['out_slot'] is not None or \
+                        'output' not in node:
                     continue
                 tail = plan[n]['store_as']
                 cout = node['output'][common_def.first_output_port(node)]['dims'][1]

@@ -429,7 +429,9 @@ def pack_dw(w):
     return w.cache['dw']
 
 
-def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, exact=False):
+def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, exact=False, hl_out=False):
+    """`hl_out`: every reader of the result is a contraction (depthwise -> pointwise): written in their (hi, lo) operand form
+    where the tile kernel takes the layer (DeviceArray.st == 'hl'), as FP32 otherwise."""
     x = as_nhwc(x)
     t, g, kh, kw = pack_dw(w)
     n, c, h, wd = x.shape
@@ -451,6 +453,16 @@ def dwconv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, e
                          pl=pads_begin[1], oh=oh, ow=ow, x_ld=x.ld, y_ld=out.ld, act=code, act_lo=lo, act_hi=hi,
                          math=_cabi.DW_EXACT if exact else _cabi.DW_AUTO, dtype=x.code)
     b = _vec_ptr(bias, c)
+    if hl_out and final is None and x.st == 'f32' and not exact and c % 8 == 0 and storage == 'f32':
+        out_hl = new_nhwc(*shape, st='hl')
+        d.y_dtype = _cabi.DT_HL
+        try:
+            _cabi.call('b200ov_dwconv2d', C.byref(d), _p(x), C.c_void_p(t.data_ptr()), _p(b), _p(out_hl), _s())
+            return out_hl
+        except _cabi.B200ovError as e:
+            if e.code != _cabi.ERR_UNSUPPORTED:
+                raise
+            d.y_dtype = 0                      # no pair-writing kernel for this shape: plain FP32 output
     _cabi.call('b200ov_dwconv2d', C.byref(d), _p(x), C.c_void_p(t.data_ptr()), _p(b), _p(out), _s())
     return _into(out, final)
 

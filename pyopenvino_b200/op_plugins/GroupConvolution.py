@@ -30,5 +30,5 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
     out_hw = common_def.spatial_output_shape((h, wd), (kh, kw), strides, pads_begin, pads_end, 'floor', auto_pad, True)
     f = fused or {}
     y = kernels.dwconv2d(x, w, strides, pads_begin, out_hw, bias=f.get('bias'), act=f.get('act'), out=f.get('out'),
-                         exact=(kernel_type == 'exact'))
+                         exact=(kernel_type == 'exact'), hl_out=bool(f.get('hl_out')))
     return plugin_util.finish(node, inputs, y)

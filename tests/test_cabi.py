@@ -43,7 +43,7 @@ def test_binding_covers_every_declared_symbol(lib_path):
     assert lib.b200ov_version() == 100
     # descriptor layouts must match the C structs (all 4-byte fields)
     assert ctypes.sizeof(_cabi.ConvDesc) == 4 * 23
-    assert ctypes.sizeof(_cabi.DwConvDesc) == 4 * 19
+    assert ctypes.sizeof(_cabi.DwConvDesc) == 4 * 20
     assert ctypes.sizeof(_cabi.PoolDesc) == 4 * 18
 
 

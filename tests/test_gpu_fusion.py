@@ -207,3 +207,30 @@ def test_models_with_hl_edges_bit_identical(model_dir, model, batch):
     assert edges[0] > 0 and edges[1] == 0, edges
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
+
+
+@pytest.mark.parametrize('shape', [(4, 32, 150, 1, 64), (3, 64, 75, 2, 128), (2, 512, 19, 1, 512), (2, 40, 11, 1, 24)])
+def test_hl_edge_depthwise_to_pointwise(shape):
+    """Depthwise 3x3 (+bias +Clamp) writing the pointwise convolution's (hi, lo) operand form: the pointwise result must be
+    bit-identical to the one computed from the FP32 depthwise output."""
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    n, c, hw, s, cout = shape
+    rng = np.random.default_rng(c * 7 + hw)
+    x = np.maximum(rng.standard_normal((n, c, hw, hw)), 0).astype(np.float32)
+    wdw = kernels.upload((rng.standard_normal((c, 1, 1, 3, 3)) * 0.3).astype(np.float32))
+    bdw = kernels.upload((0.1 * rng.standard_normal((1, c, 1, 1))).astype(np.float32))
+    wpw = kernels.upload((rng.standard_normal((cout, c, 1, 1)) * np.sqrt(2.0 / c)).astype(np.float32))
+    xd = kernels.to_nhwc(kernels.upload(x))
+    oh = (hw + 2 - 3) // s + 1
+    res = []
+    for hl in (True, False):
+        mid = kernels.dwconv2d(xd, wdw, (s, s), (1, 1), (oh, oh), bias=bdw, act=('clamp', 0.0, 6.0), hl_out=hl)
+        if not hl:
+            assert mid.st == 'f32'
+        y = kernels.conv2d(mid, wpw, (1, 1), (0, 0), (oh, oh), act=('clamp', 0.0, 6.0))
+        res.append((mid.st, np.asarray(y)))
+    assert np.array_equal(res[0][1], res[1][1]), res[0][0]
+    if n * c * oh * oh >= (1 << 16):
+        assert res[0][0] == 'hl'                # the tile kernel took it; tiny shapes fall back to FP32 (still identical)
