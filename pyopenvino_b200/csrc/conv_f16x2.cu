@@ -43,6 +43,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "f16split.cuh"
 #include "fastdiv.cuh"
@@ -242,7 +244,10 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
 // A16: the input feature map is stored as FP16 (a == a_hi: no split, 4 MMAs per slot); O16: the output is stored as FP16.
 // POOL: 1x1 convolution of MaxPool3x3/s1/p1(x) (b200ov_conv_desc.pre_pool): the producers take the 9-tap max of every
 // 8-channel run before the split, so the pooled tensor never exists (MaxPool.py:41-72: the zero padding takes part).
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false>
+// OHL: some output segment is written as (hi, lo) pairs (Params::seg_hl) -- a variant of its own so that the plain epilogue
+// keeps its register allocation (with 128-column tiles it is at the limit: the pair encoder cost 80 more spill bytes and
+// 10 % on K-short layers when it shared the code).
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false, bool OHL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* __restrict__ bias,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
@@ -799,27 +804,36 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         F16_TIMED(2, tma_store_wait_read());                     // this thread's earlier stores have read the staging buffer
         __syncwarp();
 #pragma unroll
-        for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
-          const int qb = round * L::STG_BLOCKS + sb;
-          // A segment another contraction reads is written in that kernel's operand form: per 4 channels (16 bytes)
-          // [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] -- exactly what its producers would compute from the FP32 values, once
-          // per element here instead of once per filter tap and column tile there.
-          int local_hl = 0;
-          const int sg_hl = p.seg_hl != 0 ? segment_of(n0 + qb * 32, local_hl) : -1;
-          const bool as_hl = sg_hl >= 0 && ((p.seg_hl >> sg_hl) & 1);
+        // A segment another contraction reads is written in that kernel's operand form: per 4 channels (16 bytes)
+        // [hi(c0,c1) hi(c2,c3) lo(c0,c1) lo(c2,c3)] -- exactly what its producers would compute from the FP32 values, once
+        // per element here instead of once per filter tap and column tile there (OHL variant only).
+        auto stage_blocks = [&](auto with_hl) {
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const f32x2 a0 = acc[qb * 16 + c4 * 2], a1 = acc[qb * 16 + c4 * 2 + 1];
-            chk = fma2(a0, zero2, chk);
-            chk = fma2(a1, zero2, chk);
-            const float2 u0 = unpack_f32x2(a0), u1 = unpack_f32x2(a1);
-            float4 o;
-            o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
-            o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
-            if (as_hl) o = encode_hl4(o.x, o.y, o.z, o.w);
-            *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + srow * 128 + ((c4 ^ (srow & 7)) << 4)) = o;
+          for (int sb = 0; sb < L::STG_BLOCKS; ++sb) {
+            const int qb = round * L::STG_BLOCKS + sb;
+            bool as_hl = false;
+            if constexpr (decltype(with_hl)::value) {
+              int local_hl = 0;
+              const int sg_hl = segment_of(n0 + qb * 32, local_hl);
+              as_hl = sg_hl >= 0 && ((p.seg_hl >> sg_hl) & 1);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const f32x2 a0 = acc[qb * 16 + c4 * 2], a1 = acc[qb * 16 + c4 * 2 + 1];
+              chk = fma2(a0, zero2, chk);
+              chk = fma2(a1, zero2, chk);
+              const float2 u0 = unpack_f32x2(a0), u1 = unpack_f32x2(a1);
+              float4 o;
+              o.x = fminf(fmaxf(u0.x, act_lo), act_hi); o.y = fminf(fmaxf(u0.y, act_lo), act_hi);
+              o.z = fminf(fmaxf(u1.x, act_lo), act_hi); o.w = fminf(fmaxf(u1.y, act_lo), act_hi);
+              if constexpr (decltype(with_hl)::value) {
+                if (as_hl) o = encode_hl4(o.x, o.y, o.z, o.w);
+              }
+              *reinterpret_cast<float4*>(stage_ptr + sb * 4096 + srow * 128 + ((c4 ^ (srow & 7)) << 4)) = o;
+            }
           }
-        }
+        };
+        stage_blocks(std::integral_constant<bool, OHL>{});
         if (p.tma_store) {
           fence_proxy_async();
           __syncwarp();
@@ -933,11 +947,11 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
 
 constexpr int MAX_SMEM = 227 * 1024;
 
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false>
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false, bool OHL = false>
 static int launch(const Params& p0, const void* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
                   const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s, const CUtensorMap* mx = nullptr) {
   using L = Smem<BLOCK_N, SB>;
-  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR, A16, O16, POOL>;
+  auto kern = conv_f16x2_kernel<BLOCK_N, SB, WIDE, PAIR, A16, O16, POOL, OHL>;
   static bool configured = false;
   if (!configured) {
     B200OV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL ? MAX_SMEM : L::TOTAL));
@@ -1157,6 +1171,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
     }
   }
   unsigned int* status = f16x2_status_word();
+  if (pool && p.seg_hl != 0) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool with an (hi, lo) output is not built");
   if (pool) {
     // [pixels][channels] view of x; box = 32 channels x (128 + 2w + 2) pixels, 128B swizzle, zeros outside the tensor
     p.pool_rows = f16::BLOCK_M + 2 * d->w + 2;
@@ -1170,6 +1185,18 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
     if (block_n == 96) return f16::launch<96, 2, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
     if (block_n == 64) return f16::launch<64, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
     return f16::launch<32, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+  }
+  if (p.seg_hl != 0) {
+    // (hi, lo) output: FP32 feature maps in (or the pair form itself), regular gather
+    if (a16 || o16 || p.pair4) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: no (hi, lo)-output kernel for this input");
+#define B200OV_F16_LAUNCH_HL(N_, SB_) \
+    (p.wide_loads ? f16::launch<N_, SB_, true, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s) \
+                  : f16::launch<N_, SB_, false, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s))
+    if (block_n == 128) return B200OV_F16_LAUNCH_HL(128, 4);
+    if (block_n == 96) return B200OV_F16_LAUNCH_HL(96, 4);
+    if (block_n == 64) return B200OV_F16_LAUNCH_HL(64, 6);
+    return B200OV_F16_LAUNCH_HL(32, 6);
+#undef B200OV_F16_LAUNCH_HL
   }
 #define B200OV_F16_LAUNCH2(N_, SB_, W_, P_, A_) \
   (o16 ? f16::launch<N_, SB_, W_, P_, A_, true>(p, x, bias, status, mh, ml, my, s) \
