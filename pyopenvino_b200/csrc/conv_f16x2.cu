@@ -317,6 +317,9 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while the
+  // previous kernel of the stream drains; nothing before this line reads or writes a tensor.
+  B200OV_PDL_SYNC();
 
   const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int num_stages = (p.num_slots + 1) >> 1;      // B stages per tile
@@ -1224,6 +1227,7 @@ template <int V>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
                                                             float* __restrict__ y, int m, int n, int ws_rows, int ws_ld, int ldy,
                                                             int ksplit, int act, float lo, float hi) {
+  B200OV_PDL_SYNC();
   const int ng = n / V;
   const long long total = (long long)m * ng;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {

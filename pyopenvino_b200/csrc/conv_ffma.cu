@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvP p, const float* __r
                                                        const float* __restrict__ wp,
                                                        const float* __restrict__ bias,
                                                        float* __restrict__ y) {
+  B200OV_PDL_SYNC();
   static_assert((BM / TM) * (BN / TN) == NT, "thread tiling must cover the CTA tile");
   constexpr int APAD = 4;
   __shared__ __align__(16) float As[2][BK][BM + APAD];

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(1024) detection_output_kernel(DetP p, const fl
                                                                 const float* __restrict__ conf,
                                                                 const float* __restrict__ proposals,
                                                                 float* __restrict__ out) {
+  B200OV_PDL_SYNC();
   extern __shared__ __align__(16) uint8_t det_smem[];
   float4* box = reinterpret_cast<float4*>(det_smem);
   float* score = reinterpret_cast<float*>(box + p.num_priors);

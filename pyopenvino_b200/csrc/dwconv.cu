@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(DW_TMA_THREADS, 1) dwconv3x3_tma_kernel(const 
     prefetch_tensormap(&map_x);
   }
   __syncthreads();
+  B200OV_PDL_SYNC();                     // the prologue above may overlap the previous kernel's tail
   const uint32_t my_items = p.items > blockIdx.x ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto decode = [&](uint32_t k, int& cc, int& ct, int& rt, int& ig) {
     const uint32_t item = blockIdx.x + k * gridDim.x;

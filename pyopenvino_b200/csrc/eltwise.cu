@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
                                                          const float* __restrict__ scale_vec, float scale_s,
                                                          int has_shift, const float* __restrict__ shift_vec,
                                                          float shift_s, int act, float lo, float hi) {
+  B200OV_PDL_SYNC();
   const int cg = c / V;
   const long long total = rows * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
 template <int V>
 __global__ void __launch_bounds__(256) binary_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
                                                      float* __restrict__ y, long long count) {
+  B200OV_PDL_SYNC();
   const long long total = count / V;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -77,6 +79,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // one CTA (128 threads) per row
 __global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int cols) {
+  B200OV_PDL_SYNC();
   __shared__ float red[4];
   __shared__ float bcast;
   const float* xr = x + (long long)blockIdx.x * cols;
@@ -107,6 +110,7 @@ __device__ __forceinline__ float lrn_pow(float v, float beta);
 __global__ void __launch_bounds__(256) lrn_kernel(const float* __restrict__ x, float* __restrict__ y, long long pixels,
                                                   int c, int x_ld, int y_ld, int half, float alpha, float beta,
                                                   float bias) {
+  B200OV_PDL_SYNC();
   const long long total = pixels * c;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -141,6 +145,7 @@ template <int HALF, typename T = float>
 __global__ void __launch_bounds__(256) lrn_vec4_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t total,
                                                        FastDiv d_cg, int x_ld, int y_ld, int half_rt, float alpha,
                                                        float beta, float bias) {
+  B200OV_PDL_SYNC();
   const int half = HALF > 0 ? HALF : half_rt;
   const int cg = (int)d_cg.d;
   const uint32_t stride = gridDim.x * blockDim.x;

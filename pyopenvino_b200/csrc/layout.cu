@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TIN* __restrict__ 
                                                         int has_scale, const float* __restrict__ scale_vec,
                                                         float scale_s, int has_shift,
                                                         const float* __restrict__ shift_vec, float shift_s) {
+  B200OV_PDL_SYNC();
   __shared__ float tile[32][33];
   long long bid = blockIdx.x;
   const int tc = (int)(bid % tiles_c);
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TIN* __r
                                                                   const float* __restrict__ scale_vec, float scale_s,
                                                                   int has_shift, const float* __restrict__ shift_vec,
                                                                   float shift_s) {
+  B200OV_PDL_SYNC();
   float sc[MAXC], sf[MAXC];
 #pragma unroll
   for (int ch = 0; ch < MAXC; ++ch) {
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) nchw8_to_nhwc4_x4_kernel(const TIN* __res
                                                                 const float* __restrict__ scale_vec, float scale_s,
                                                                 int has_shift, const float* __restrict__ shift_vec,
                                                                 float shift_s) {
+  B200OV_PDL_SYNC();
   float sc[4], sf[4];
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(256) nchw8_to_nhwc4_x4_kernel(const TIN* __res
 template <int V>
 __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                      long long rows, int cols, int src_ld, int dst_ld) {
+  B200OV_PDL_SYNC();
   const int cg = cols / V;
   const long long total = rows * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
 template <typename TIN, typename TOUT>
 __global__ void __launch_bounds__(256) copy2d_cast_kernel(const TIN* __restrict__ src, TOUT* __restrict__ dst, long long rows, int cols,
                                                           int src_ld, int dst_ld) {
+  B200OV_PDL_SYNC();
   // two elements per thread where the row pitch allows (cols, src_ld, dst_ld even): 32-bit / 64-bit accesses
   const long long total = rows * cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -260,6 +265,7 @@ static int input_to_nhwc_split_typed(const TIN* x, float* y, int n, int c, int h
 // plain (non 4-D) inputs: widen only
 template <typename TIN>
 __global__ void __launch_bounds__(256) widen_kernel(const TIN* __restrict__ x, float* __restrict__ y, long long count) {
+  B200OV_PDL_SYNC();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     y[i] = load_widen(x + i);
 }

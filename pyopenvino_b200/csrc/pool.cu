@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(POOL_TMA_THREADS, 1) pool_max_tma_kernel(const
     prefetch_tensormap(&map_x);
   }
   __syncthreads();
+  B200OV_PDL_SYNC();                     // the prologue above may overlap the previous kernel's tail
   const uint32_t my_items = p.items > blockIdx.x ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto decode = [&](uint32_t k, int& cc, int& ct, int& rt, int& ig) {
     const uint32_t item = blockIdx.x + k * gridDim.x;
@@ -332,6 +333,7 @@ __device__ __forceinline__ void storev_t(T* p, const float (&v)[V]) {
 template <int V, typename T = float>
 __global__ void __launch_bounds__(256) pool_kernel(PoolP p, const T* __restrict__ x, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, T* __restrict__ y) {
+  B200OV_PDL_SYNC();
   const int cg = p.c / V;
   const long long total = (long long)p.n * p.oh * p.ow * cg;
   const int hp = p.h + p.pt + p.pb, wpad = p.w + p.pl + p.pr;
