@@ -118,6 +118,7 @@ struct Params {
   // by TMA from the [pixels][channels] view of x, in a ring of pool_stages stages of pool_stage_bytes.
   int pool_rows, pool_stage_bytes, pool_stages;
   FastDiv d_pool_stages;
+  int bias_n;                          // bias[(column) % bias_n]: the real C_out (pixel-group stems repeat the bias per group member)
   int a_hl;                            // 1: x already holds the FP16 (hi, scaled lo) pairs (network input written by the layout
                                        //    kernel, b200ov_input_to_nhwc_split): the producers only route words, no split
   FastDiv d_ohow, d_ow, d_upt, d_kw, d_tiles_n, d_slots, d_ksplit;
@@ -244,10 +245,13 @@ __device__ __forceinline__ Run8 load_run8(const float* p, bool wide) {
 // A16: the input feature map is stored as FP16 (a == a_hi: no split, 4 MMAs per slot); O16: the output is stored as FP16.
 // POOL: 1x1 convolution of MaxPool3x3/s1/p1(x) (b200ov_conv_desc.pre_pool): the producers take the 9-tap max of every
 // 8-channel run before the split, so the pooled tensor never exists (MaxPool.py:41-72: the zero padding takes part).
+// POOL == 2 ("staged"): a plain 1x1 / stride-1 convolution whose pixel tiles take the same road -- TMA into the shared-memory ring
+// (no halo), 128-bit shared loads in the producers -- so that the latency of a feature map streamed from HBM / L2 is hidden by
+// the ring (5..7 tiles of 16 KB in flight per SM) instead of by what two producer sets keep in flight in registers.
 // OHL: some output segment is written as (hi, lo) pairs (Params::seg_hl) -- a variant of its own so that the plain epilogue
 // keeps its register allocation (with 128-column tiles it is at the limit: the pair encoder cost 80 more spill bytes and
 // 10 % on K-short layers when it shared the code).
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false, bool OHL = false>
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, int POOL = 0, bool OHL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* __restrict__ bias,
                   unsigned int* __restrict__ status, const __grid_constant__ CUtensorMap map_hi,
@@ -466,7 +470,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         const uint32_t tile = blockIdx.x + (uint32_t)tl * gridDim.x;
         uint32_t m_blk_, n_blk_, ksp_;
         tile_coord(p, tile, m_blk_, n_blk_, ksp_);
-        const int r0 = (int)m_blk_ * BLOCK_M - p.w - 1;
+        const int r0 = (int)m_blk_ * BLOCK_M - (POOL == 1 ? p.w + 1 : 0);
         for (int slot = 0; slot < p.num_slots; ++slot) {
           mbar_wait(bar_pool_empty(st), phase ^ 1);
           if (elect_one_sync()) {
@@ -524,7 +528,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           rix[r] = (int)ox * p.sw - p.pl;
           rbase[r] = x + ((long long)((int)img * p.h + riy[r]) * p.w + rix[r]) * p.x_ld;
           if constexpr (POOL) {
-            prow[r] = (m - m0) + p.w + 1;
+            prow[r] = (m - m0) + (POOL == 1 ? p.w + 1 : 0);
             pflag[r] = m < p.M ? (16 | (oy > 0 ? 1 : 0) | ((int)oy + 1 < p.h ? 2 : 0) | (ox > 0 ? 4 : 0) | ((int)ox + 1 < p.w ? 8 : 0)) : 0;
           }
         }
@@ -540,6 +544,24 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         p.d_pool_stages.divmod(item, round, st);
         mbar_wait(bar_pool_full(st), round & 1);
         const uint32_t sbase = base + L::POOL_RING + st * p.pool_stage_bytes;
+        if constexpr (POOL == 2) {
+          // staged 1x1: the thread's four pixels x 8 channels, two 128-bit loads each; odd pixel groups read their upper half
+          // first (bank layout, see below).  Rows past M and channels past C_in are TMA's zero fill.
+          const int hswap2 = rsub & 1;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = prow[r];
+            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4 + hswap2) ^ (row & 7)) << 4);
+            float4 t0, t1;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0.x), "=f"(t0.y), "=f"(t0.z), "=f"(t0.w) : "r"(a));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t1.x), "=f"(t1.y), "=f"(t1.z), "=f"(t1.w) : "r"(a ^ 16u));
+            const float4 lo4 = hswap2 ? t1 : t0, hi4 = hswap2 ? t0 : t1;
+            dst[r].v[0] = lo4.x; dst[r].v[1] = lo4.y; dst[r].v[2] = lo4.z; dst[r].v[3] = lo4.w;
+            dst[r].v[4] = hi4.x; dst[r].v[5] = hi4.y; dst[r].v[6] = hi4.z; dst[r].v[7] = hi4.w;
+          }
+          pool_release = bar_pool_empty(st);
+          return;
+        }
         // The four windows cover 6 pixel columns (linear neighbours p - 1 .. p + 4 of the thread's first pixel p) x 3 image rows:
         // 18 pixel positions instead of 36.  Column maxima first (vertical), then each output takes its three columns.  A
         // vertical tap outside the image is aliased to the centre row; a horizontal neighbour that belongs to another image row
@@ -547,6 +569,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         // is exact because such a pixel takes the zero padding into its max anyway (MaxPool.py:41-72).  Rows past M sit beyond
         // the tensor map's pixel dimension and read TMA's zero fill.
         float4 cm[6][2];
+        const int hswap = rsub & 1;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           const int f = pflag[c == 0 ? 0 : (c == 5 ? 3 : c - 1)];
@@ -555,7 +578,11 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const int row = rowc + (dy == 0 ? ((f & 1) ? -p.w : 0) : (dy == 1 ? 0 : ((f & 2) ? p.w : 0)));
-            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4) ^ (row & 7)) << 4);
+            // Bank layout: the eight lanes of a 128-bit shared-memory wavefront are two pixel groups (rsub, rsub + 1: box rows 4
+            // apart, so their swizzle terms differ by 4) x four units.  With every lane reading its lower 16-byte half first
+            // the two groups hit the same four chunk columns (a two-way conflict on each of the 36 loads: ncu, r2n); odd
+            // groups therefore read their upper half first and the halves are swapped back when the outputs are formed.
+            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4 + hswap) ^ (row & 7)) << 4);
 #ifdef B200OV_POOL_EXP_1TAP
             if (dy != 1) { t[dy][0] = t[dy][1] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
 #endif
@@ -578,6 +605,12 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
             dst[r].v[4 * hf + 0] = B200OV_OUT(x); dst[r].v[4 * hf + 1] = B200OV_OUT(y);
             dst[r].v[4 * hf + 2] = B200OV_OUT(z); dst[r].v[4 * hf + 3] = B200OV_OUT(w);
 #undef B200OV_OUT
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {            // odd pixel groups loaded channels 4..7 first
+            const float lo4 = dst[r].v[i], hi4 = dst[r].v[4 + i];
+            dst[r].v[i] = hswap ? hi4 : lo4;
+            dst[r].v[4 + i] = hswap ? lo4 : hi4;
           }
         }
         // The stage is released in convert_store, after the tcgen05.st that consume every value loaded here: an arrive placed
@@ -705,7 +738,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
       const int m0 = (int)m_blk * BLOCK_M, n0 = (int)n_blk * BLOCK_N;
       const int row_off = (int)ksp * p.ws_rows;                 // split-K: this split's block of workspace rows
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);                 // everyone is done with the previous tile's bias
-      if (e < BLOCK_N) sbias[e] = (bias != nullptr && n0 + e < p.cout) ? __ldg(bias + n0 + e) : 0.f;
+      if (e < BLOCK_N) sbias[e] = (bias != nullptr && n0 + e < p.cout) ? __ldg(bias + (n0 + e) % p.bias_n) : 0.f;
       named_bar_sync(EPI_BAR_ID, NUM_EPILOGUE);
       // FP32 accumulators as packed pairs (FADD2 / FFMA2 halve the issue slots), initialised with the bias
       f32x2 acc[BLOCK_N / 2];
@@ -886,8 +919,12 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
 
 // OIHW -> [plane hi | plane lo], each [coutp][kpad] halfs, K ordered (slot, kappa) with the in-slot permutation
 // the A producers use: kappa = 16*b + 4*u + j  <->  unit 4*slot + u, channel 4*b + j of that unit.
+// Pixel-group form (group > 1, pair layout only): row n' = j * cout + n of the packed matrix is filter n seen from the j-th of
+// `group` horizontally adjacent output pixels -- the same taps moved `shift` tap pairs to the right inside a window of
+// upt = upt0 + (group - 1) * shift pairs, zeros elsewhere (see conv2d_f16x2_multi).
 __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int kh,
-                                        int kw, int coutp, int kpad, int upt, int units, int pair4, int kx0) {
+                                        int kw, int coutp, int kpad, int upt, int units, int pair4, int kx0, int group = 1,
+                                        int shift = 0) {
   const long long plane = (long long)coutp * kpad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < plane;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -897,10 +934,11 @@ __global__ void pack_f16_weights_kernel(const float* __restrict__ w, __half* __r
     const int unit = slot * 4 + ((kappa & 15) >> 2);
     const int cj = ((kappa >> 4) << 2) + (kappa & 3);
     float v = 0.f;
-    if (n < cout && unit < units) {
+    if (n < cout * group && unit < units) {
       if (pair4) {                       // unit = (filter row ky, tap pair kxp): taps kx0 + 2*kxp, kx0 + 2*kxp + 1, 4 channels each
-        const int ky = unit / upt, kx = kx0 + 2 * (unit - ky * upt) + (cj >> 2), c = cj & 3;
-        if (kx >= 0 && kx < kw && c < cin) v = w[(((long long)n * cin + c) * kh + ky) * kw + kx];
+        const int j = n / cout, nf = n - j * cout;
+        const int ky = unit / upt, kx = kx0 + 2 * (unit - ky * upt - j * shift) + (cj >> 2), c = cj & 3;
+        if (kx >= 0 && kx < kw && c < cin && unit - ky * upt >= j * shift) v = w[(((long long)nf * cin + c) * kh + ky) * kw + kx];
       } else {
         const int tap = unit / upt, c = (unit - tap * upt) * 8 + cj;
         if (c < cin) {
@@ -950,7 +988,7 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, cons
 
 constexpr int MAX_SMEM = 227 * 1024;
 
-template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, bool POOL = false, bool OHL = false>
+template <int BLOCK_N, int SB, bool WIDE, bool PAIR, bool A16, bool O16, int POOL = 0, bool OHL = false>
 static int launch(const Params& p0, const void* x, const float* bias, unsigned int* status, const CUtensorMap& mh,
                   const CUtensorMap& ml, const CUtensorMap* my, cudaStream_t s, const CUtensorMap* mx = nullptr) {
   using L = Smem<BLOCK_N, SB>;
@@ -994,10 +1032,43 @@ void f16_weight_dims(int cout, int cin, int kh, int kw, int* coutp, int* kpad, i
   if (units) *units = n_units;
 }
 
+// Pixel-group forms of a C_in <= 4 stem with horizontal stride 2 (conv2d_f16x2_multi): `group` horizontally adjacent output
+// pixels are one GEMM row with group * cout columns over a window of upt + group - 1 tap pairs.  Groups of 2 .. max are
+// packed (the call picks the largest one that divides the output width); f16_group_max returns 1 when there is none.
+int f16_group_max(int cout, int cin) {
+  if (cin > 4 || cout % 8 != 0 || cout > 64) return 1;
+  int group = 128 / round_up(cout, 32);
+  if (group > 4) group = 4;
+  return group;
+}
+void f16_group_dims(int group, int cout, int kh, int kw, int* coutp, int* kpad, int* upt, int* units) {
+  const int u = ceil_div(kw + 1, 2) + group - 1;
+  if (coutp) *coutp = group * cout;
+  if (kpad) *kpad = round_up(kh * u, 8) * 8;
+  if (upt) *upt = u;
+  if (units) *units = kh * u;
+}
+// halfs from the start of the f16 section to group form `group`, tap alignment `al`
+static long long f16_group_offset(int group, int al, int cout, int cin, int kh, int kw) {
+  int coutp, kpad;
+  f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, nullptr, nullptr);
+  long long off = 4LL * coutp * kpad;
+  for (int g = 2; g <= group; ++g) {
+    int gc, gk;
+    f16_group_dims(g, cout, kh, kw, &gc, &gk, nullptr, nullptr);
+    if (g < group) off += 4LL * gc * gk;
+    else off += 2LL * al * gc * gk;
+  }
+  return off;
+}
+
 long long f16_section_floats(int cout, int cin, int kh, int kw) {
   int coutp, kpad;
   f16_weight_dims(cout, cin, kh, kw, &coutp, &kpad, nullptr, nullptr);
-  return (long long)coutp * kpad * (cin <= 4 ? 2 : 1);   // two planes of halfs (x two tap alignments for the pair layout)
+  long long n = (long long)coutp * kpad * (cin <= 4 ? 2 : 1);   // two planes of halfs (x two tap alignments for the pair layout)
+  const int gmax = f16_group_max(cout, cin);
+  if (gmax > 1) n = f16_group_offset(gmax + 1, 0, cout, cin, kh, kw) / 2;      // + every pixel-group form, both alignments
+  return n;
 }
 
 int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh, int kw, cudaStream_t s) {
@@ -1011,6 +1082,16 @@ int pack_f16_weights(const float* w_oihw, float* out, int cout, int cin, int kh,
     f16::pack_f16_weights_kernel<<<bw_grid((long long)coutp * kpad, 256), 256, 0, s>>>(
         w_oihw, reinterpret_cast<__half*>(out) + 2LL * coutp * kpad, cout, cin, kh, kw, coutp, kpad, upt, units, 1, -1);
     B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
+    for (int group = 2; group <= f16_group_max(cout, cin); ++group) {
+      int gcoutp, gkpad, gupt, gunits;
+      f16_group_dims(group, cout, kh, kw, &gcoutp, &gkpad, &gupt, &gunits);
+      for (int al = 0; al < 2; ++al) {
+        f16::pack_f16_weights_kernel<<<bw_grid((long long)gcoutp * gkpad, 256), 256, 0, s>>>(
+            w_oihw, reinterpret_cast<__half*>(out) + f16_group_offset(group, al, cout, cin, kh, kw), cout, cin, kh, kw, gcoutp, gkpad,
+            gupt, gunits, 1, -al, group, 1);
+        B200OV_LAUNCH_CHECK("pack_f16_weights_kernel");
+      }
+    }
   }
   return B200OV_OK;
 }
@@ -1113,35 +1194,61 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
     p.num_slots = round_up(ceil_div(p.num_slots, ksplit), 2);     // whole weight stages; the last split's tail reads zeros
   }
   p.ksplit = ksplit; p.ws_rows = ksplit > 1 ? ws_rows : 0;
-  // Tile width: 128 columns, or 96 where that needs no more tiles (C_out in (64, 96], (128, 192], (256, 288]): an
-  // N = 96 MMA takes 56 cycles against 64 for N = 128 (tools/ubench/mma_rate.cu), a 96-wide tile leaves TMEM room
-  // for a second cross-term accumulator, and e.g. C_out = 192 is two full tiles instead of one and a half.
-  int block_n = d->cout > 64 ? 128 : (d->cout > 32 ? 64 : 32);
-  if (d->cout > 64 && ceil_div(d->cout, 96) == ceil_div(d->cout, 128)) block_n = 96;
-  if (const char* e = getenv("B200OV_F16_FORCE_N")) {                  // developer knob (tile-width experiments)
-    const int v = atoi(e);
-    if (v == 32 || v == 64 || v == 96 || v == 128) block_n = v;
-  }
-  p.tiles_n = ceil_div(d->cout, block_n);
-  const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n * ksplit;
-  if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
-  p.num_tiles = (int)tiles;
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
+  p.bias_n = d->cout;
   p.pair4 = d->cin <= 4 && !a16;
   const __half* hi_plane = reinterpret_cast<const __half*>(wt);
-  int kw_eff = d->kw;
+  int kw_eff = d->kw, ow_eff = d->ow;
   if (p.pair4 && d->sw % 2 == 0 && d->w % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0) {
     // Stem with an even horizontal stride on an even-width image (pixel pitch 4 floats): two adjacent pixels are one
     // 32-byte aligned "super-pixel" of 8 channels, and with the tap pairs aligned to even pixel columns (pairs start at
     // tap -(pl & 1); the packed weights hold both alignments) the stem is an ordinary 8-channel convolution over the
     // [h][w/2][8] view: kernel kh x upt, horizontal stride sw/2, left padding ceil(pl/2).  The producers then run the
     // regular path (one 256-bit load per row and unit, one bounds test) instead of the two-half pair gather.
-    if (d->pl & 1) hi_plane += 2LL * coutp * kpad;
     p.pair4 = 0;
     p.w = d->w / 2; p.x_ld = 8; p.sw = d->sw / 2; p.pl = (d->pl + 1) / 2;
+    // Pixel groups: with C_out <= 64 a 128-row tile would issue N <= 64 MMAs, which cost as much pipe time as N ~ 100
+    // (52 cycles against 64 for N = 128), and every output pixel would gather its own kh x upt window.  `group` horizontally
+    // adjacent output pixels (stride 2 = one super-pixel apart) share all but group - 1 of their tap-pair columns, so they
+    // run as ONE GEMM row: group * C_out columns over a window of upt + group - 1 pairs, member j's filter shifted j pairs
+    // (zeros elsewhere; packed at load).  The [M / group][group * C_out] result is the same memory as [M][C_out].  7x7 / s2
+    // stem, C_out 64: 9 slots per two pixels instead of 14, N = 128; SSD 3x3 / s2 stem, C_out 32: 4 slots per four pixels
+    // instead of 8.
+    int group = f16_group_max(d->cout, d->cin);
+    if (const char* e = getenv("B200OV_F16_STEM_GROUP")) { const int v = atoi(e); if (v >= 1 && v < group) group = v; }   // developer knob
+    while (group > 1 && d->ow % group != 0) --group;
+    if (group > 1 && d->sw == 2 && nseg == 1 && segs[0].cout == d->cout && segs[0].y_ld == d->cout && p.seg_hl == 0 && !o16 &&
+        ksplit == 1) {
+      int gcoutp, gkpad, gupt, gunits;
+      f16_group_dims(group, d->cout, d->kh, d->kw, &gcoutp, &gkpad, &gupt, &gunits);
+      hi_plane += f16_group_offset(group, d->pl & 1, d->cout, d->cin, d->kh, d->kw);
+      coutp = gcoutp; kpad = gkpad; units = gunits; upt = gupt;
+      p.units = units;
+      p.num_slots = ceil_div(units, 4);
+      p.cout = group * d->cout;
+      p.M = p.M / group;
+      p.sw = group;                                    // super-pixels per GEMM row
+      p.seg_cout[0] = p.cout; p.seg_yld[0] = p.cout;
+      ow_eff = d->ow / group;
+    } else if (d->pl & 1) {
+      hi_plane += 2LL * coutp * kpad;
+    }
     kw_eff = upt;
     upt = 1;
   }
+  // Tile width: 128 columns, or 96 where that needs no more tiles (C_out in (64, 96], (128, 192], (256, 288]): an
+  // N = 96 MMA takes 56 cycles against 64 for N = 128 (tools/ubench/mma_rate.cu), a 96-wide tile leaves TMEM room
+  // for a second cross-term accumulator, and e.g. C_out = 192 is two full tiles instead of one and a half.
+  int block_n = p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32);
+  if (p.cout > 64 && ceil_div(p.cout, 96) == ceil_div(p.cout, 128)) block_n = 96;
+  if (const char* e = getenv("B200OV_F16_FORCE_N")) {                  // developer knob (tile-width experiments)
+    const int v = atoi(e);
+    if (v == 32 || v == 64 || v == 96 || v == 128) block_n = v;
+  }
+  p.tiles_n = ceil_div(p.cout, block_n);
+  const long long tiles = (long long)ceil_div(p.M, f16::BLOCK_M) * p.tiles_n * ksplit;
+  if (tiles * p.num_slots > 0x7fffffffLL) return set_error(B200OV_ERR_INVALID, "conv2d: problem too large");
+  p.num_tiles = (int)tiles;
   // Optional L2 prefetch of what a producer set gathers next (same rows, 16 units further along the channel run), only
   // where that stays inside one filter tap and the four lanes of a pixel cover one 128-byte line.  +4..10 % on layers
   // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
@@ -1156,7 +1263,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   if (p.a_hl && p.pair4) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: a pre-split input needs the super-pixel stem path");
   p.wide_loads = !a16 && !p.pair4 && (p.x_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31u) == 0);
   if (a16) p.prefetch = 0;
-  p.d_ohow = FastDiv(d->oh * d->ow); p.d_ow = FastDiv(d->ow); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
+  p.d_ohow = FastDiv(d->oh * ow_eff); p.d_ow = FastDiv(ow_eff); p.d_upt = FastDiv(upt); p.d_kw = FastDiv(kw_eff);
   p.d_tiles_n = FastDiv(p.tiles_n); p.d_slots = FastDiv(p.num_slots); p.d_ksplit = FastDiv(ksplit);
   const __half* lo_plane = hi_plane + (long long)coutp * kpad;
   CUtensorMap mh, ml, my[3];
@@ -1166,8 +1273,8 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   if (rc) return rc;
   for (int i = 0; i < 3; ++i) {
     if (p.tma_store && i < nseg && !o16) {
-      rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, segs[i].cout,
-                            ksplit > 1 ? (long long)ksplit * ws_rows : (long long)p.M, (long long)segs[i].y_ld * 4, 32, 32);
+      rc = f16::make_map_2d(&my[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, segs[i].y, p.seg_cout[i],
+                            ksplit > 1 ? (long long)ksplit * ws_rows : (long long)p.M, (long long)p.seg_yld[i] * 4, 32, 32);
       if (rc) return rc;
     } else {
       my[i] = mh;    // never dereferenced
@@ -1175,6 +1282,27 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   }
   unsigned int* status = f16x2_status_word();
   if (pool && p.seg_hl != 0) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool with an (hi, lo) output is not built");
+  // Staged 1x1 (POOL == 2): pixel tiles of a plain 1x1 / stride-1 convolution (or MatMul) over an FP32 map go through the same
+  // TMA ring as the pooled variant, without the halo.  B200OV_F16_STAGE=0 switches it off (A/B measurements).
+  bool stage = !pool && d->pre_pool == B200OV_PREPOOL_NONE && d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 &&
+               d->pl == 0 && d->oh == d->h && d->ow == d->w && d->x_dtype == B200OV_DT_F32 && !o16 && !a16 && d->cin % 8 == 0 &&
+               ksplit == 1 && !p.pair4 && (p.x_ld % 4 == 0) && d->cin >= f16::SLOT_K;
+  if (const char* e = getenv("B200OV_F16_STAGE")) { if (atoi(e) == 0) stage = false; }
+  if (stage) {
+    p.pool_rows = f16::BLOCK_M;
+    p.pool_stage_bytes = f16::BLOCK_M * 128;
+    CUtensorMap mx;
+    rc = f16::make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, d->cin, (long long)p.M, (long long)d->x_ld * 4, f16::SLOT_K, p.pool_rows);
+    if (rc) return rc;
+#define B200OV_F16_LAUNCH_ST(N_, SB_) \
+    (p.seg_hl != 0 ? f16::launch<N_, SB_, false, false, false, false, 2, true>(p, x, bias, status, mh, ml, my, s, &mx) \
+                   : f16::launch<N_, SB_, false, false, false, false, 2, false>(p, x, bias, status, mh, ml, my, s, &mx))
+    if (block_n == 128) return B200OV_F16_LAUNCH_ST(128, 2);
+    if (block_n == 96) return B200OV_F16_LAUNCH_ST(96, 2);
+    if (block_n == 64) return B200OV_F16_LAUNCH_ST(64, 4);
+    return B200OV_F16_LAUNCH_ST(32, 4);
+#undef B200OV_F16_LAUNCH_ST
+  }
   if (pool) {
     // [pixels][channels] view of x; box = 32 channels x (128 + 2w + 2) pixels, 128B swizzle, zeros outside the tensor
     p.pool_rows = f16::BLOCK_M + 2 * d->w + 2;
@@ -1184,17 +1312,17 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
     rc = f16::make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, d->cin, (long long)p.M, (long long)d->x_ld * 4, f16::SLOT_K, p.pool_rows);
     if (rc) return rc;
     // a two-stage weight ring leaves room for the pixel tiles (the layer is bandwidth-bound: the MMA warp never waits on B)
-    if (block_n == 128) return f16::launch<128, 2, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
-    if (block_n == 96) return f16::launch<96, 2, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
-    if (block_n == 64) return f16::launch<64, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
-    return f16::launch<32, 4, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s, &mx);
+    if (block_n == 128) return f16::launch<128, 2, false, false, false, false, 1>(p, x, bias, status, mh, ml, my, s, &mx);
+    if (block_n == 96) return f16::launch<96, 2, false, false, false, false, 1>(p, x, bias, status, mh, ml, my, s, &mx);
+    if (block_n == 64) return f16::launch<64, 4, false, false, false, false, 1>(p, x, bias, status, mh, ml, my, s, &mx);
+    return f16::launch<32, 4, false, false, false, false, 1>(p, x, bias, status, mh, ml, my, s, &mx);
   }
   if (p.seg_hl != 0) {
     // (hi, lo) output: FP32 feature maps in (or the pair form itself), regular gather
     if (a16 || o16 || p.pair4) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: no (hi, lo)-output kernel for this input");
 #define B200OV_F16_LAUNCH_HL(N_, SB_) \
-    (p.wide_loads ? f16::launch<N_, SB_, true, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s) \
-                  : f16::launch<N_, SB_, false, false, false, false, false, true>(p, x, bias, status, mh, ml, my, s))
+    (p.wide_loads ? f16::launch<N_, SB_, true, false, false, false, 0, true>(p, x, bias, status, mh, ml, my, s) \
+                  : f16::launch<N_, SB_, false, false, false, false, 0, true>(p, x, bias, status, mh, ml, my, s))
     if (block_n == 128) return B200OV_F16_LAUNCH_HL(128, 4);
     if (block_n == 96) return B200OV_F16_LAUNCH_HL(96, 4);
     if (block_n == 64) return B200OV_F16_LAUNCH_HL(64, 6);
