@@ -504,9 +504,9 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     int riy[4], rix[4];
     int prow[4], pflag[4];             // POOL: box row of the window centre; bits: 1 up, 2 down, 4 left, 8 right neighbour inside the image, 16 row < M
     uint32_t cur_tl = 0xffffffffu, cur_slot0 = 0;
-    uint32_t pool_release = 0;         // POOL: "stage consumed" barrier of the item between issue_loads and convert_store
+    uint32_t pool_release[2] = {0, 0};   // POOL: "stage consumed" barriers of the items between issue_loads and convert_store
     F16_TRACE_DECL
-    auto issue_loads = [&](uint32_t item, Run8 (&dst)[4]) {
+    auto issue_loads = [&](uint32_t item, Run8 (&dst)[4], const int which = 0) {
       uint32_t tl, slot;
       p.d_slots.divmod(item, tl, slot);
       if (tl != cur_tl) {
@@ -520,7 +520,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         for (int r = 0; r < 4; ++r) {
           // POOL: the thread's four rows are four CONSECUTIVE pixels (tile row 16g + 8h + rsub <-> pixel 4 rsub + 2g + h of the
           // warp's 32), so their 3x3 windows share columns; the epilogue undoes the permutation when it stages the tile
-          const int m = POOL ? m0 + 32 * q + 4 * rsub + r : m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
+          const int m = POOL == 1 ? m0 + 32 * q + 4 * rsub + r : m0 + 32 * q + 16 * (r >> 1) + rsub + 8 * (r & 1);
           uint32_t img, rem, oy, ox;
           p.d_ohow.divmod((uint32_t)(m < p.M ? m : 0), img, rem);
           p.d_ow.divmod(rem, oy, ox);
@@ -545,21 +545,18 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         mbar_wait(bar_pool_full(st), round & 1);
         const uint32_t sbase = base + L::POOL_RING + st * p.pool_stage_bytes;
         if constexpr (POOL == 2) {
-          // staged 1x1: the thread's four pixels x 8 channels, two 128-bit loads each; odd pixel groups read their upper half
-          // first (bank layout, see below).  Rows past M and channels past C_in are TMA's zero fill.
-          const int hswap2 = rsub & 1;
+          // staged 1x1: the thread's four rows (the register-gather kernel's row mapping) x 8 channels, two 128-bit loads each.
+          // The eight lanes of a shared-memory wavefront are two neighbouring rows x four units: their swizzle terms differ in
+          // bit 0, so they cover all eight 16-byte columns (no bank conflict).  Rows past M and channels past C_in are TMA's
+          // zero fill.
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int row = prow[r];
-            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4 + hswap2) ^ (row & 7)) << 4);
-            float4 t0, t1;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0.x), "=f"(t0.y), "=f"(t0.z), "=f"(t0.w) : "r"(a));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t1.x), "=f"(t1.y), "=f"(t1.z), "=f"(t1.w) : "r"(a ^ 16u));
-            const float4 lo4 = hswap2 ? t1 : t0, hi4 = hswap2 ? t0 : t1;
-            dst[r].v[0] = lo4.x; dst[r].v[1] = lo4.y; dst[r].v[2] = lo4.z; dst[r].v[3] = lo4.w;
-            dst[r].v[4] = hi4.x; dst[r].v[5] = hi4.y; dst[r].v[6] = hi4.z; dst[r].v[7] = hi4.w;
+            const uint32_t a = sbase + (uint32_t)row * 128u + ((uint32_t)((2 * u4) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[r].v[0]), "=f"(dst[r].v[1]), "=f"(dst[r].v[2]), "=f"(dst[r].v[3]) : "r"(a));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[r].v[4]), "=f"(dst[r].v[5]), "=f"(dst[r].v[6]), "=f"(dst[r].v[7]) : "r"(a ^ 16u));
           }
-          pool_release = bar_pool_empty(st);
+          pool_release[which] = bar_pool_empty(st);
           return;
         }
         // The four windows cover 6 pixel columns (linear neighbours p - 1 .. p + 4 of the thread's first pixel p) x 3 image rows:
@@ -617,7 +614,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         // here is not ordered behind the LDS still queued in the (saturated) shared-memory pipe -- it overtook them and the
         // loader's refill of the stage then raced the last loads of the window (seen as wrong fourth pixels of a group on the
         // first item of a tile, when the loader is already waiting for the stage).
-        pool_release = bar_pool_empty(st);
+        pool_release[which] = bar_pool_empty(st);
       } else if constexpr (!PAIR) {
         uint32_t tap, cu, ky, kx;
         p.d_upt.divmod(unit, tap, cu);
@@ -656,7 +653,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         }
       }
     };
-    auto convert_store = [&](uint32_t item, const Run8 (&src)[4]) {
+    auto convert_store = [&](uint32_t item, const Run8 (&src)[4], const int which = 0) {
       const int as = item % A_SLOTS;
       F16_WAIT(0, bar_a_empty(as), ((item / A_SLOTS) & 1) ^ 1);
       if (q == 0 && lane == 0) F16_STAMP(1, item);
@@ -692,7 +689,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         split_pair(r1.v[6], r1.v[7], v[7], v[15]);
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
-      if constexpr (POOL) mbar_arrive(pool_release);       // (after the stores: see issue_loads)
+      if constexpr (POOL) mbar_arrive(pool_release[which]);       // (after the stores: see issue_loads)
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
       __syncwarp();
@@ -702,17 +699,17 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     Run8 d0[4], d1[4];
     for (uint32_t item = 2 * set; item < total_items; item += 2 * NUM_SETS) {
       const bool two = item + 1 < total_items;
-      if constexpr (POOL) {
+      if constexpr (POOL == 1) {
         // shared-memory gather: nothing to overlap with a second item's loads, and one buffer leaves the registers to the window
         issue_loads(item, d0);
         convert_store(item, d0);
         if (two) { issue_loads(item + 1, d0); convert_store(item + 1, d0); }
         continue;
       }
-      F16_TIMED(1, issue_loads(item, d0); if (two) issue_loads(item + 1, d1));
+      F16_TIMED(1, issue_loads(item, d0, 0); if (two) issue_loads(item + 1, d1, 1));
       if (q == 0 && lane == 0) { F16_STAMP(0, item); F16_STAMP(0, item + 1); }
-      F16_TIMED(3, convert_store(item, d0));
-      if (two) F16_TIMED(4, convert_store(item + 1, d1));
+      F16_TIMED(3, convert_store(item, d0, 0));
+      if (two) F16_TIMED(4, convert_store(item + 1, d1, 1));
     }
     F16_TRACE_STORE(2, warp == W_PRODUCER0 && lane == 0);
   } else {
@@ -726,7 +723,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     uint8_t* stage_ptr = base_ptr + L::STAGING + q * L::STG_BLOCKS * 4096;
     uint32_t chunkcount = 0;
     // staging row of this thread's accumulator lane: the pixel order (POOL: the producers' permutation undone, see there)
-    const int srow = POOL ? 4 * (lane & 7) + (lane >> 3) : lane;
+    const int srow = POOL == 1 ? 4 * (lane & 7) + (lane >> 3) : lane;
     f32x2 chk = pack_f32x2(0.f, 0.f);
     const float act_lo = p.act == B200OV_ACT_NONE ? -INFINITY : (p.act == B200OV_ACT_RELU ? 0.f : p.lo);
     const float act_hi = p.act == B200OV_ACT_CLAMP ? p.hi : INFINITY;
@@ -1004,7 +1001,8 @@ static int launch(const Params& p0, const void* x, const float* bias, unsigned i
     // the pixel-tile ring takes what the weight ring and the output staging leave of the SM's shared memory
     int stages = (MAX_SMEM - 1024 - L::POOL_RING) / p.pool_stage_bytes;
     if (stages > L::POOL_MAX_STAGES) stages = L::POOL_MAX_STAGES;
-    if (stages < 2) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool tile ring does not fit in shared memory");
+    // (staged 1x1: each producer set holds the stages of two items at a time)
+    if (stages < (POOL == 2 ? 4 : 2)) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pixel-tile ring does not fit in shared memory");
     p.pool_stages = stages;
     p.d_pool_stages = FastDiv(stages);
     smem = L::POOL_RING + stages * p.pool_stage_bytes + 1024;
@@ -1284,8 +1282,10 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   if (pool && p.seg_hl != 0) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool with an (hi, lo) output is not built");
   // Staged 1x1 (POOL == 2): pixel tiles of a plain 1x1 / stride-1 convolution (or MatMul) over an FP32 map go through the same
   // TMA ring as the pooled variant, without the halo.  B200OV_F16_STAGE=0 switches it off (A/B measurements).
+  bool hl_stage = false;                 // (hi, lo)-pair inputs too (the producers then only route words): opt-in, B200OV_F16_STAGE=2
+  if (const char* e = getenv("B200OV_F16_STAGE")) hl_stage = atoi(e) == 2;
   bool stage = !pool && d->pre_pool == B200OV_PREPOOL_NONE && d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1 && d->pt == 0 &&
-               d->pl == 0 && d->oh == d->h && d->ow == d->w && d->x_dtype == B200OV_DT_F32 && !o16 && !a16 && d->cin % 8 == 0 &&
+               d->pl == 0 && d->oh == d->h && d->ow == d->w && (d->x_dtype == B200OV_DT_F32 || (d->x_dtype == B200OV_DT_HL && hl_stage)) && !o16 && !a16 && d->cin % 8 == 0 &&
                ksplit == 1 && !p.pair4 && (p.x_ld % 4 == 0) && d->cin >= f16::SLOT_K;
   if (const char* e = getenv("B200OV_F16_STAGE")) { if (atoi(e) == 0) stage = false; }
   if (stage) {
