@@ -630,8 +630,10 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
           } else {
             dst[r] = load_run8(ok ? reinterpret_cast<const float*>(rbase[r] + off) : g_zero_run, WIDE);
             // the same rows, 16 units (4 slots) further along the channels of this tap: what this set gathers next
+#ifdef B200OV_F16_PREFETCH_BUILD     // developer build only: the predicated-off prefetches still cost 13 issue slots per item
             if (p.prefetch && u4 == 0 && ok && cu + 16 < p.d_upt.d)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase[r] + off + 128));
+#endif
           }
         }
       } else {
@@ -1250,7 +1252,7 @@ int conv2d_f16x2_multi(const b200ov_conv_desc* d, const void* x, const float* wt
   // Optional L2 prefetch of what a producer set gathers next (same rows, 16 units further along the channel run), only
   // where that stays inside one filter tap and the four lanes of a pixel cover one 128-byte line.  +4..10 % on layers
   // with long channel runs when the input comes from HBM (micro-benchmarks with a flushed L2), nothing inside the models,
-  // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1.
+  // where the producing layer left the input in L2 -- so it is opt-in: B200OV_F16_PREFETCH=1 in a -DB200OV_F16_PREFETCH_BUILD build.
   { const char* e = getenv("B200OV_F16_PREFETCH"); p.prefetch = (e && atoi(e) != 0 && !p.pair4 && upt % 4 == 0 && upt > 16) ? 1 : 0; }
   const bool pool = d->pre_pool == B200OV_PREPOOL_MAX3X3S1;
   if (d->pre_pool != B200OV_PREPOOL_NONE &&
