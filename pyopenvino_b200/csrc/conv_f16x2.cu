@@ -298,16 +298,16 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_main_full(i), 1);
-      mbar_init(bar_main_empty(i), NUM_EPILOGUE);
+      mbar_init(bar_main_empty(i), NUM_EPILOGUE / 32);     // one arrival per warp: 32 lanes arriving on one mbarrier are 32 serialised shared-memory atomics
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_cross_full(i), 1);
-      mbar_init(bar_cross_empty(i), NUM_EPILOGUE);
+      mbar_init(bar_cross_empty(i), NUM_EPILOGUE / 32);
     }
     if constexpr (POOL) {
       for (int i = 0; i < p.pool_stages; ++i) {
         mbar_init(bar_pool_full(i), 1);
-        mbar_init(bar_pool_empty(i), SET_THREADS);
+        mbar_init(bar_pool_empty(i), SET_THREADS / 32);
       }
       prefetch_tensormap(&map_x);
     }
@@ -691,7 +691,13 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         split_pair(r1.v[6], r1.v[7], v[7], v[15]);
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
-      if constexpr (POOL) mbar_arrive(pool_release[which]);       // (after the stores: see issue_loads)
+      if constexpr (POOL) {
+        // (after the stores: see issue_loads.)  One arrival per warp, behind a __syncwarp: every lane has issued the stores
+        // that consume its loads.  Per-lane arrivals were 32 serialised atomics on one shared-memory word -- as many conflict
+        // wavefronts per item as the staged variant's loads themselves (ncu, r2r).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pool_release[which]);
+      }
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
       __syncwarp();
@@ -762,7 +768,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         }
         tc_fence_before();
         if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_M0 + buf, NUM_EPILOGUE + 32); }
-        else mbar_arrive(bar_main_empty(buf));
+        else { __syncwarp(); if (lane == 0) mbar_arrive(bar_main_empty(buf)); }
         if (warp == W_EPILOGUE0 && lane == 0) F16_STAMP(7, chunkcount);
         ++chunkcount;
       };
@@ -782,7 +788,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
       }
       tc_fence_before();
       if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_X, NUM_EPILOGUE + 32); }
-      else mbar_arrive(bar_cross_empty(xb));
+      else { __syncwarp(); if (lane == 0) mbar_arrive(bar_cross_empty(xb)); }
       promote();
       // activation (None / ReLU / Clamp as one clamp with infinite bounds), staged in shared memory in the
       // 128B-swizzled box layout TMA expects, STG_BLOCKS 32-column blocks per round.  chk turns NaN as soon
