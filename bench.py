@@ -174,7 +174,7 @@ def kernel_of(kind):
     if kind.startswith('conv') or kind == 'matmul':
         return 'conv_f16x2_kernel'
     return {'depthwise': 'dwconv3x3_tma_kernel', 'maxpool': 'pool_max_tma_kernel', 'lrn': 'lrn_vec4_kernel',
-            'input_layout': 'nchw_to_nhwc_smallc_kernel'}.get(kind, kind)
+            'input_layout': 'nchw_to_nhwc4_x4_kernel'}.get(kind, kind)
 
 
 def layer_table(exe, in_name, x, peaks):

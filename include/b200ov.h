@@ -277,6 +277,10 @@ int b200ov_copy2d_st(const void* src, int src_dtype, void* dst, int dst_dtype, i
                      int src_ld, int dst_ld, void* stream);
 /* rows x cols strided copy (Concat.py:9-13 when producers could not write in place). */
 int b200ov_copy2d(const float* src, float* dst, int64_t rows, int cols, int src_ld, int dst_ld, void* stream);
+/* Concat of `nparts` (<= B200OV_CONCAT_MAX_PARTS) dense row blocks along the columns in one launch: dst[r][off_p + c] = srcs[p][r][c],
+ * dst dense with sum(cols) columns (Concat.py:9-13, `np.concatenate(..., axis)` with everything before `axis` folded into rows). */
+#define B200OV_CONCAT_MAX_PARTS 8
+int b200ov_concat_rows(int nparts, const float* const* srcs, const int* cols, float* dst, int64_t rows, void* stream);
 
 /* ---- SSD DetectionOutput ------------------------------------------------------------------------ */
 typedef struct {

@@ -14,6 +14,7 @@ ACT_NONE, ACT_RELU, ACT_CLAMP, ACT_SIGMOID = 0, 1, 2, 3
 MATH_AUTO, MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_F16X2, MATH_SAFE = 0, 1, 2, 3, 4, 5
 POOL_MAX, POOL_AVG_REF = 0, 1
 DT_F32, DT_F16, DT_U8, DT_I8, DT_HL = 0, 1, 2, 3, 4
+CONCAT_MAX_PARTS = 8                 # B200OV_CONCAT_MAX_PARTS
 
 
 class B200ovError(RuntimeError):
@@ -102,6 +103,7 @@ SIGNATURES = {
     'b200ov_input_to_nhwc_split': [_P, _I, _P, _I, _I, _I, _I, _P, _F, _I, _P, _F, _P],
     'b200ov_widen': [_P, _I, _P, _L, _P],
     'b200ov_copy2d': [_P, _P, _L, _I, _I, _I, _P],
+    'b200ov_concat_rows': [_I, _P, _P, _P, _L, _P],
     'b200ov_detection_output': [C.POINTER(DetectionDesc), _P, _P, _P, _P, _P],
 }
 NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
@@ -111,7 +113,7 @@ launch_count = 0          # kernels launched through this binding (bench.py repo
 
 _LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_matmul_ws', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
               'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_lrn_st', 'b200ov_transpose', 'b200ov_transpose_st', 'b200ov_copy2d_st',
-              'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_input_to_nhwc_split', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_detection_output'}
+              'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_input_to_nhwc_split', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_concat_rows', 'b200ov_detection_output'}
 
 
 def load():

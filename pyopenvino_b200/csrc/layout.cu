@@ -116,14 +116,35 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const TIN* __r
   }
 }
 
-// The same for 1-byte inputs (uint8 / int8), four adjacent pixels per thread: one 32-bit load per plane (128 B per
-// warp and plane instead of 32 B) and four 128-bit stores.  Needs hw % 4 == 0, a 4-byte aligned source and y_ld == 4.
+// The same with four adjacent pixels per thread: one vector load per plane (16 bytes of FP32, 8 of FP16, 4 of uint8 / int8:
+// 512 / 256 / 128 bytes per warp and plane instead of 128 / 64 / 32) and four 128-bit stores (2 KB contiguous per warp).
+// SPLIT: the stem contraction's pre-split (hi, lo) pair form instead of FP32 (see PAD == 44 above; same bits).
+// Needs hw % 4 == 0, a source aligned to four elements and y_ld == 4.
 template <typename TIN>
-__global__ void __launch_bounds__(256) nchw8_to_nhwc4_x4_kernel(const TIN* __restrict__ x, float* __restrict__ y,
-                                                                long long quads, int c, int hw, int has_scale,
-                                                                const float* __restrict__ scale_vec, float scale_s,
-                                                                int has_shift, const float* __restrict__ shift_vec,
-                                                                float shift_s) {
+__device__ __forceinline__ void load4_widen(const TIN* p, float (&f)[4]) {
+  if constexpr (sizeof(TIN) == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  } else if constexpr (sizeof(TIN) == 2) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __half2 a = *reinterpret_cast<const __half2*>(&t.x), b = *reinterpret_cast<const __half2*>(&t.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  } else {
+    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(p));
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const uint32_t b = (word >> (8 * px)) & 0xffu;
+      f[px] = TIN(-1) < TIN(0) ? (float)(int8_t)b : (float)b;
+    }
+  }
+}
+
+template <typename TIN, bool SPLIT>
+__global__ void __launch_bounds__(256) nchw_to_nhwc4_x4_kernel(const TIN* __restrict__ x, float* __restrict__ y,
+                                                               long long quads, int c, int hw, int has_scale,
+                                                               const float* __restrict__ scale_vec, float scale_s,
+                                                               int has_shift, const float* __restrict__ shift_vec,
+                                                               float shift_s) {
   B200OV_PDL_SYNC();
   float sc[4], sf[4];
 #pragma unroll
@@ -139,24 +160,41 @@ __global__ void __launch_bounds__(256) nchw8_to_nhwc4_x4_kernel(const TIN* __res
     float v[4][4];                                   // [pixel][channel]
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      uint32_t word = 0;
-      if (ch < c) word = __ldg(reinterpret_cast<const uint32_t*>(xp + (long long)ch * hw));
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ch < c) {
+        load4_widen(xp + (long long)ch * hw, f);
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        float f = 0.f;
-        if (ch < c) {
-          const uint32_t b = (word >> (8 * px)) & 0xffu;
-          f = sizeof(TIN) == 1 && TIN(-1) < TIN(0) ? (float)(int8_t)b : (float)b;
-          if (has_scale) f = __fmul_rn(f, sc[ch]);
-          if (has_shift) f = __fadd_rn(f, sf[ch]);
+        for (int px = 0; px < 4; ++px) {
+          if (has_scale) f[px] = __fmul_rn(f[px], sc[ch]);
+          if (has_shift) f[px] = __fadd_rn(f[px], sf[ch]);
         }
-        v[px][ch] = f;
       }
-    }
-    float4* yp = reinterpret_cast<float4*>(y + (img * hw + r) * 4);
 #pragma unroll
-    for (int px = 0; px < 4; ++px) yp[px] = make_float4(v[px][0], v[px][1], v[px][2], v[px][3]);
+      for (int px = 0; px < 4; ++px) v[px][ch] = f[px];
+    }
+    uint4* yp = reinterpret_cast<uint4*>(y + (img * hw + r) * 4);
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint4 o;
+      if constexpr (SPLIT) {
+        __half h[4], l[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) split_f16x2(v[px][ch], h[ch], l[ch]);
+        const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+        const __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+        o.x = *reinterpret_cast<const uint32_t*>(&h01); o.y = *reinterpret_cast<const uint32_t*>(&h23);
+        o.z = *reinterpret_cast<const uint32_t*>(&l01); o.w = *reinterpret_cast<const uint32_t*>(&l23);
+      } else {
+        o.x = __float_as_uint(v[px][0]); o.y = __float_as_uint(v[px][1]); o.z = __float_as_uint(v[px][2]); o.w = __float_as_uint(v[px][3]);
+      }
+      yp[px] = o;
+    }
   }
+}
+
+template <typename TIN>
+static bool x4_ok(const TIN* x, const float* y, int hw, int y_ld) {
+  return y_ld == 4 && aligned16(y) && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & (4 * sizeof(TIN) - 1)) == 0;
 }
 
 template <int V>
@@ -173,6 +211,31 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
       *reinterpret_cast<float4*>(dst + r * dst_ld + c0) = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c0));
     else
       dst[r * dst_ld + c0] = __ldg(src + r * src_ld + c0);
+  }
+}
+
+// Concat of up to B200OV_CONCAT_MAX_PARTS row blocks in ONE launch: dst[r][off_p + c] = src_p[r][c].  The 2-D Concats of the SSD heads
+// (six [n][h*w*273] class-score blocks -> [n][1917*91]) were six launches of a few microseconds of work each.
+struct ConcatP {
+  const float* src[B200OV_CONCAT_MAX_PARTS];
+  int cols[B200OV_CONCAT_MAX_PARTS], off[B200OV_CONCAT_MAX_PARTS + 1];
+  int nparts, total;
+};
+template <int V>
+__global__ void __launch_bounds__(256) concat_rows_kernel(const ConcatP p, float* __restrict__ dst, long long rows) {
+  B200OV_PDL_SYNC();
+  const int tg = p.total / V;
+  const long long total = rows * tg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / tg;
+    const int c0 = (int)(idx - r * tg) * V;
+    int part = 0;
+#pragma unroll
+    for (int i = 1; i < B200OV_CONCAT_MAX_PARTS; ++i)
+      if (i < p.nparts && c0 >= p.off[i]) part = i;
+    const float* sp = p.src[part] + r * p.cols[part] + (c0 - p.off[part]);
+    if constexpr (V == 4) *reinterpret_cast<float4*>(dst + r * p.total + c0) = __ldg(reinterpret_cast<const float4*>(sp));
+    else dst[r * p.total + c0] = __ldg(sp);
   }
 }
 
@@ -223,13 +286,11 @@ static int input_to_nhwc_typed(const TIN* x, float* y, int n, int c, int hw, int
                                float scale_s, int has_shift, const float* shift_vec, float shift_s, cudaStream_t s) {
   if (c <= 4) {
     const long long pixels = (long long)n * hw;
-    if constexpr (sizeof(TIN) == 1) {
-      if (y_ld == 4 && aligned16(y) && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3u) == 0) {
-        launch_k(nchw8_to_nhwc4_x4_kernel<TIN>, bw_grid(pixels / 4, 256), 256, 0, s, x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
-                                                                              has_shift, shift_vec, shift_s);
-        B200OV_LAUNCH_CHECK("nchw8_to_nhwc4_x4_kernel");
-        return B200OV_OK;
-      }
+    if (x4_ok(x, y, hw, y_ld)) {
+      launch_k(nchw_to_nhwc4_x4_kernel<TIN, false>, bw_grid(pixels / 4, 256), 256, 0, s, x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
+                                                                                  has_shift, shift_vec, shift_s);
+      B200OV_LAUNCH_CHECK("nchw_to_nhwc4_x4_kernel");
+      return B200OV_OK;
     }
     if (y_ld == 8 && aligned16(y))
       launch_k(nchw_to_nhwc_smallc_kernel<4, 8, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, y_ld, has_scale, scale_vec,
@@ -256,6 +317,12 @@ template <typename TIN>
 static int input_to_nhwc_split_typed(const TIN* x, float* y, int n, int c, int hw, int has_scale, const float* scale_vec, float scale_s,
                                      int has_shift, const float* shift_vec, float shift_s, cudaStream_t s) {
   const long long pixels = (long long)n * hw;
+  if (x4_ok(x, y, hw, 4)) {
+    launch_k(nchw_to_nhwc4_x4_kernel<TIN, true>, bw_grid(pixels / 4, 256), 256, 0, s, x, y, pixels / 4, c, hw, has_scale, scale_vec, scale_s,
+                                                                               has_shift, shift_vec, shift_s);
+    B200OV_LAUNCH_CHECK("nchw_to_nhwc4_x4_kernel");
+    return B200OV_OK;
+  }
   launch_k(nchw_to_nhwc_smallc_kernel<4, 44, TIN>, bw_grid(pixels, 256), 256, 0, s, x, y, pixels, c, hw, 4, has_scale, scale_vec, scale_s,
                                                                             has_shift, shift_vec, shift_s);
   B200OV_LAUNCH_CHECK("nchw_to_nhwc_smallc_kernel");
@@ -370,6 +437,29 @@ int b200ov_widen(const void* x, int dtype, float* y, int64_t count, void* stream
     default: return set_error(B200OV_ERR_INVALID, "widen: unknown element type %d", dtype);
   }
   B200OV_LAUNCH_CHECK("widen_kernel");
+  return B200OV_OK;
+}
+
+int b200ov_concat_rows(int nparts, const float* const* srcs, const int* cols, float* dst, int64_t rows, void* stream) {
+  B200OV_REQUIRE(srcs && cols && dst && rows >= 0 && nparts >= 1 && nparts <= B200OV_CONCAT_MAX_PARTS, "concat_rows: bad argument");
+  ConcatP p;
+  memset(&p, 0, sizeof(p));
+  p.nparts = nparts;
+  bool vec = aligned16(dst);
+  long long off = 0;
+  for (int i = 0; i < nparts; ++i) {
+    B200OV_REQUIRE(srcs[i] && cols[i] > 0, "concat_rows: bad part %d", i);
+    p.src[i] = srcs[i]; p.cols[i] = cols[i]; p.off[i] = (int)off;
+    off += cols[i];
+    vec = vec && cols[i] % 4 == 0 && aligned16(srcs[i]);
+  }
+  B200OV_REQUIRE(off <= 0x7fffffffLL, "concat_rows: row too long");
+  p.off[nparts] = p.total = (int)off;
+  if (rows == 0) return B200OV_OK;
+  cudaStream_t s = as_stream(stream);
+  if (vec) launch_k(concat_rows_kernel<4>, bw_grid(rows * (p.total / 4), 256), 256, 0, s, p, dst, (long long)rows);
+  else launch_k(concat_rows_kernel<1>, bw_grid(rows * p.total, 256), 256, 0, s, p, dst, (long long)rows);
+  B200OV_LAUNCH_CHECK("concat_rows_kernel");
   return B200OV_OK;
 }
 

@@ -48,10 +48,16 @@ def compute(node: dict, inputs: dict = None, kernel_type: str = 'naive', debug: 
         outer = int(np.prod(shape[:axis])) if axis > 0 else 1
         inner_total = int(np.prod(shape[axis:]))
         out = DeviceArray(dev.alloc_f32(outer * inner_total), shape, 'plain')
-        off = 0
-        for p in parts:
-            inner = int(np.prod(p.shape[axis:]))
-            _cabi.call('b200ov_copy2d', C.c_void_p(p.ptr), C.c_void_p(out.ptr + 4 * off), outer, inner, inner, inner_total,
-                       C.c_void_p(dev.stream()))
-            off += inner
+        inners = [int(np.prod(p.shape[axis:])) for p in parts]
+        if len(parts) <= _cabi.CONCAT_MAX_PARTS:
+            # one launch for all parts (the SSD head Concats have six)
+            srcs = (C.c_void_p * len(parts))(*[p.ptr for p in parts])
+            cols = (C.c_int * len(parts))(*inners)
+            _cabi.call('b200ov_concat_rows', len(parts), srcs, cols, C.c_void_p(out.ptr), outer, C.c_void_p(dev.stream()))
+        else:
+            off = 0
+            for p, inner in zip(parts, inners):
+                _cabi.call('b200ov_copy2d', C.c_void_p(p.ptr), C.c_void_p(out.ptr + 4 * off), outer, inner, inner, inner_total,
+                           C.c_void_p(dev.stream()))
+                off += inner
     return plugin_util.finish(node, inputs, out)

@@ -140,3 +140,26 @@ def test_pixel_group_stems_vs_oracle(shape):
         outs[g] = got
     # the grouped forms only reorder zero terms inside the K run: tiny differences at most
     assert np.abs(outs['4'] - outs['1']).max() <= 1e-5 + 1e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('shapes,axis', [
+    ([(3, 1083 * 7), (3, 600 * 7), (3, 150 * 7), (3, 54 * 7), (3, 24 * 7), (3, 6 * 7)], 1),     # SSD head Concat: one launch
+    ([(2, 8, 16), (2, 12, 16), (2, 4, 16)], 1),                                                # vector path, inner dims folded
+    ([(5, 3)] * 9, 1),                                                                         # more parts than one launch takes
+    ([(4, 10), (4, 1)], 1),
+])
+def test_row_concat_one_launch_bit_exact(shapes, axis):
+    """Concat.py:9-13 on device-resident non-NHWC parts: b200ov_concat_rows must equal np.concatenate bit for bit."""
+    from pyopenvino_b200 import _cabi, kernels
+    from pyopenvino_b200.inference_engine import IECore
+    plugins = IECore().plugins.plugins
+    rng = np.random.default_rng(len(shapes))
+    parts = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    node = {'name': 'cat', 'type': 'Concat', 'data': {'axis': str(axis)},
+            'input': {i: {'precision': 'FP32', 'dims': p.shape} for i, p in enumerate(parts)},
+            'output': {len(parts): {'precision': 'FP32', 'dims': ()}}}
+    launches0 = _cabi.launch_count
+    got = plugins['Concat'].compute(node, {i: kernels.upload(p) for i, p in enumerate(parts)})[len(parts)]
+    if len(parts) <= _cabi.CONCAT_MAX_PARTS:
+        assert _cabi.launch_count - launches0 == 1
+    assert np.array_equal(np.asarray(got), np.concatenate(parts, axis=axis))

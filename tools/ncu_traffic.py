@@ -13,7 +13,7 @@ import json
 import os
 import sys
 
-KERNELS = ['conv_f16x2_kernel', 'dwconv3x3_tma_kernel', 'pool_max_tma_kernel', 'dwconv3x3_strip_kernel', 'pool_max_strip_kernel', 'lrn_vec4_kernel', 'nchw_to_nhwc_smallc_kernel',
+KERNELS = ['conv_f16x2_kernel', 'dwconv3x3_tma_kernel', 'pool_max_tma_kernel', 'dwconv3x3_strip_kernel', 'pool_max_strip_kernel', 'lrn_vec4_kernel', 'nchw_to_nhwc4_x4_kernel', 'nchw_to_nhwc_smallc_kernel',
            'conv_tcgen05_kernel', 'conv_ffma_kernel', 'detection_output_kernel', 'copy2d_kernel', 'affine_act_kernel', 'transpose_kernel',
            'pool_kernel', 'softmax_kernel']
 
