@@ -299,6 +299,12 @@ typedef struct {
  * Decisions and record order are bit-compatible with the reference's float32 python arithmetic. */
 int b200ov_detection_output(const b200ov_detection_desc* d, const float* loc, const float* conf,
                             const float* proposals, float* out, void* stream);
+/* The same with a caller-provided scratch buffer of b200ov_detection_output_workspace() bytes (8-byte aligned): the top-1 class
+ * per prior (DetectionOutput.py:69-94) then runs as a grid-wide kernel over the whole batch before the per-image CTAs.
+ * Same records bit for bit. */
+int b200ov_detection_output_workspace(const b200ov_detection_desc* d, size_t* bytes);
+int b200ov_detection_output_ws(const b200ov_detection_desc* d, const float* loc, const float* conf,
+                               const float* proposals, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,8 @@ SIGNATURES = {
     'b200ov_copy2d': [_P, _P, _L, _I, _I, _I, _P],
     'b200ov_concat_rows': [_I, _P, _P, _P, _L, _P],
     'b200ov_detection_output': [C.POINTER(DetectionDesc), _P, _P, _P, _P, _P],
+    'b200ov_detection_output_workspace': [C.POINTER(DetectionDesc), C.POINTER(_Z)],
+    'b200ov_detection_output_ws': [C.POINTER(DetectionDesc), _P, _P, _P, _P, _P, _Z, _P],
 }
 NON_STATUS = {'b200ov_version': ([], _I), 'b200ov_last_error': ([], C.c_char_p)}
 
@@ -113,7 +115,7 @@ launch_count = 0          # kernels launched through this binding (bench.py repo
 
 _LAUNCHING = {'b200ov_pack_conv_weights', 'b200ov_conv2d', 'b200ov_conv2d_multi', 'b200ov_matmul', 'b200ov_matmul_ws', 'b200ov_pack_dw_weights', 'b200ov_dwconv2d',
               'b200ov_pool2d', 'b200ov_affine_act', 'b200ov_binary', 'b200ov_softmax', 'b200ov_lrn', 'b200ov_lrn_st', 'b200ov_transpose', 'b200ov_transpose_st', 'b200ov_copy2d_st',
-              'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_input_to_nhwc_split', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_concat_rows', 'b200ov_detection_output'}
+              'b200ov_nchw_to_nhwc_affine', 'b200ov_input_to_nhwc', 'b200ov_input_to_nhwc_split', 'b200ov_widen', 'b200ov_copy2d', 'b200ov_concat_rows', 'b200ov_detection_output', 'b200ov_detection_output_ws'}
 
 
 def load():

@@ -596,5 +596,11 @@ def detection_output(loc, conf, proposals, num_classes, keep_top_k, center_size,
                             code_center_size=int(center_size), variance_encoded_in_target=int(variance_in_target),
                             clip_before_nms=int(clip_before), clip_after_nms=int(clip_after),
                             confidence_threshold=conf_thr, nms_threshold=nms_thr)
-    _cabi.call('b200ov_detection_output', C.byref(d), _p(loc), _p(conf), _p(proposals), _p(out), _s())
+    # scratch for the batch-wide top-1 pass: (score, class) per prior
+    nbytes = C.c_size_t(0)
+    _cabi.call('b200ov_detection_output_workspace', C.byref(d), C.byref(nbytes))
+    ws = dev.alloc_f32((nbytes.value + 3) // 4)
+    _cabi.call('b200ov_detection_output_ws', C.byref(d), _p(loc), _p(conf), _p(proposals), _p(out), C.c_void_p(ws.data_ptr()),
+               C.c_size_t(nbytes.value), _s())
+    _cabi.launch_count += 1              # two kernels: the batch-wide top-1 pass and the per-image CTAs
     return out

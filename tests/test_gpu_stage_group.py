@@ -163,3 +163,33 @@ def test_row_concat_one_launch_bit_exact(shapes, axis):
     if len(parts) <= _cabi.CONCAT_MAX_PARTS:
         assert _cabi.launch_count - launches0 == 1
     assert np.array_equal(np.asarray(got), np.concatenate(parts, axis=axis))
+
+
+def test_detection_output_batch_wide_top1_pass_same_records():
+    """b200ov_detection_output_ws (grid-wide top-1 pass + per-image CTAs) against the single-kernel entry point: same
+    records bit for bit (DetectionOutput.py:162-300; the golden-vector tests pin the ws path to the reference)."""
+    import ctypes as C
+    from pyopenvino_b200 import _cabi, kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(11)
+    n, priors, classes, keep = 5, 1917, 91, 100
+    loc = (0.5 * rng.standard_normal((n, priors * 4))).astype(np.float32)
+    conf = (1.0 / (1.0 + np.exp(-(rng.standard_normal((n, priors * classes)) * 2 - 3)))).astype(np.float32)
+    conf[:, ::7] = conf[:, 3::7]                   # exact ties between classes and between priors
+    cx, cy = rng.random(priors), rng.random(priors)
+    w, h = 0.05 + 0.3 * rng.random(priors), 0.05 + 0.3 * rng.random(priors)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], axis=1).astype(np.float32)
+    var = np.tile(np.float32([0.1, 0.1, 0.2, 0.2]), (priors, 1))
+    prop = np.stack([boxes.reshape(-1), var.reshape(-1)])[None].astype(np.float32)
+    ld, cd, pd = kernels.upload(loc), kernels.upload(conf), kernels.upload(prop)
+    got = np.asarray(kernels.detection_output(ld, cd, pd, classes, keep, True, False, False, True, 0.3, 0.6))
+    out = kernels.upload(np.zeros((n * keep, 7), np.float32))
+    d = _cabi.DetectionDesc(n=n, num_priors=priors, num_classes=classes, keep_top_k=keep, code_center_size=1,
+                            variance_encoded_in_target=0, clip_before_nms=0, clip_after_nms=1,
+                            confidence_threshold=0.3, nms_threshold=0.6)
+    _cabi.call('b200ov_detection_output', C.byref(d), C.c_void_p(ld.ptr), C.c_void_p(cd.ptr), C.c_void_p(pd.ptr), C.c_void_p(out.ptr),
+               C.c_void_p(dev.stream()))
+    want = np.asarray(out).reshape(got.shape)
+    assert np.array_equal(got, want)
+    assert (got[0, 0, :, 0] >= 0).sum() > n        # the case really produces detections
