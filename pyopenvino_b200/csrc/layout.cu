@@ -224,18 +224,20 @@ struct ConcatP {
 template <int V>
 __global__ void __launch_bounds__(256) concat_rows_kernel(const ConcatP p, float* __restrict__ dst, long long rows) {
   B200OV_PDL_SYNC();
+  // blockIdx.y walks the rows, the threads of a row walk its columns: no division per element
   const int tg = p.total / V;
-  const long long total = rows * tg;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / tg;
-    const int c0 = (int)(idx - r * tg) * V;
-    int part = 0;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    float* drow = dst + r * p.total;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < tg; g += gridDim.x * blockDim.x) {
+      const int c0 = g * V;
+      int part = 0;
 #pragma unroll
-    for (int i = 1; i < B200OV_CONCAT_MAX_PARTS; ++i)
-      if (i < p.nparts && c0 >= p.off[i]) part = i;
-    const float* sp = p.src[part] + r * p.cols[part] + (c0 - p.off[part]);
-    if constexpr (V == 4) *reinterpret_cast<float4*>(dst + r * p.total + c0) = __ldg(reinterpret_cast<const float4*>(sp));
-    else dst[r * p.total + c0] = __ldg(sp);
+      for (int i = 1; i < B200OV_CONCAT_MAX_PARTS; ++i)
+        if (i < p.nparts && c0 >= p.off[i]) part = i;
+      const float* sp = p.src[part] + r * p.cols[part] + (c0 - p.off[part]);
+      if constexpr (V == 4) *reinterpret_cast<float4*>(drow + c0) = __ldg(reinterpret_cast<const float4*>(sp));
+      else drow[c0] = __ldg(sp);
+    }
   }
 }
 
@@ -457,8 +459,14 @@ int b200ov_concat_rows(int nparts, const float* const* srcs, const int* cols, fl
   p.off[nparts] = p.total = (int)off;
   if (rows == 0) return B200OV_OK;
   cudaStream_t s = as_stream(stream);
-  if (vec) launch_k(concat_rows_kernel<4>, bw_grid(rows * (p.total / 4), 256), 256, 0, s, p, dst, (long long)rows);
-  else launch_k(concat_rows_kernel<1>, bw_grid(rows * p.total, 256), 256, 0, s, p, dst, (long long)rows);
+  const int v = vec ? 4 : 1;
+  const int gy = (int)(rows < 4096 ? rows : 4096);
+  int gx = ceil_div(p.total / v, 256 * 4);                    // ~4 elements per thread and row
+  const int cap = ceil_div(bw_grid(rows * (p.total / v), 256), gy);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  if (vec) launch_k(concat_rows_kernel<4>, dim3(gx, gy), 256, 0, s, p, dst, (long long)rows);
+  else launch_k(concat_rows_kernel<1>, dim3(gx, gy), 256, 0, s, p, dst, (long long)rows);
   B200OV_LAUNCH_CHECK("concat_rows_kernel");
   return B200OV_OK;
 }
