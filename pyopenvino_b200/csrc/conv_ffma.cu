@@ -7,6 +7,8 @@
 // register-prefetching the next slice while the current one is multiplied (2-stage pipeline).
 // This is the exact-FP32 path: it serves the tiny-K stem layers (C_in = 1 / 3), odd shapes, and
 // is the in-library cross-check for the tcgen05 3xTF32 path (gemm_tcgen05.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ov {
@@ -234,6 +236,47 @@ static int launch_cfg(const ConvP& p0, bool vec, const float* x, const float* wp
   return B200OV_OK;
 }
 
+// C_in = 1 stems (MNIST: 28 x 28 x 1 -> 32 / 64 channels, K = 9 / 25): the layer is an output-write stream (K FMAs per 4 bytes
+// written), which the tiled implicit GEMM above turns into 16-wide K slices of mostly padding (mnist_bn conv2d at batch 1024:
+// 0.101 ms for 103 MB of output).  Direct form: C_out / 4 consecutive threads own one output pixel (a float4 of channels each,
+// so a warp writes 512 contiguous bytes), the taps come from L1 and the filter from shared memory.  Same FP32 FMA arithmetic
+// class as conv_ffma_kernel (taps accumulated in (ky, kx) order, bias added last).
+constexpr int C1_MAX_TAPS = 49, C1_MAX_COUT = 64;
+__global__ void __launch_bounds__(256) conv_c1_direct_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ wp,
+                                                             const float* __restrict__ bias, float* __restrict__ y) {
+  B200OV_PDL_SYNC();
+  __shared__ __align__(16) float ws[C1_MAX_TAPS * C1_MAX_COUT];
+  const int taps = p.kh * p.kw, cg = p.cout >> 2;
+  for (int i = threadIdx.x; i < taps * p.cout; i += blockDim.x) ws[i] = __ldg(wp + (long long)(i / p.cout) * p.ldw + (i % p.cout));
+  __syncthreads();
+  const long long total = (long long)p.M * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / cg), c0 = (int)(idx - (long long)m * cg) * 4;
+    const int img = m / p.ohow, r = m - img * p.ohow;
+    const int oy = r / p.ow, ox = r - oy * p.ow;
+    const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
+    const float* xi = x + (long long)img * p.h * p.w * p.x_ld;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = iy0 + ky;
+      if ((unsigned)iy >= (unsigned)p.h) continue;             // zero padding (Convolution.py:63)
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = ix0 + kx;
+        if ((unsigned)ix >= (unsigned)p.w) continue;
+        const float v = __ldg(xi + ((long long)iy * p.w + ix) * p.x_ld);
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + (ky * p.kw + kx) * p.cout + c0);
+        acc.x = fmaf(v, w4.x, acc.x); acc.y = fmaf(v, w4.y, acc.y); acc.z = fmaf(v, w4.z, acc.z); acc.w = fmaf(v, w4.w, acc.w);
+      }
+    }
+    if (bias != nullptr) {
+      acc.x += __ldg(bias + c0); acc.y += __ldg(bias + c0 + 1); acc.z += __ldg(bias + c0 + 2); acc.w += __ldg(bias + c0 + 3);
+    }
+    acc.x = apply_act(acc.x, p.act, p.lo, p.hi); acc.y = apply_act(acc.y, p.act, p.lo, p.hi);
+    acc.z = apply_act(acc.z, p.act, p.lo, p.hi); acc.w = apply_act(acc.w, p.act, p.lo, p.hi);
+    *reinterpret_cast<float4*>(y + (long long)m * p.y_ld + c0) = acc;
+  }
+}
+
 int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
                 cudaStream_t s) {
   ConvP p;
@@ -248,6 +291,12 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
   p.nb_n = 1;
   if (p.M == 0) return B200OV_OK;
+  if (d->cin == 1 && d->cout % 4 == 0 && d->cout <= C1_MAX_COUT && d->kh * d->kw <= C1_MAX_TAPS && d->y_ld % 4 == 0 && aligned16(y) &&
+      getenv("B200OV_NO_C1_DIRECT") == nullptr) {
+    launch_k(conv_c1_direct_kernel, bw_grid((long long)p.M * (d->cout / 4), 256), 256, 0, s, p, x, wp, bias, y);
+    B200OV_LAUNCH_CHECK("conv_c1_direct_kernel");
+    return B200OV_OK;
+  }
   const bool vec = (d->cin % 4 == 0) && (d->x_ld % 4 == 0) && aligned16(x);
   const int sms = props().sm_count;
   if (d->cout <= 32) return launch_cfg<128, 32, 4, 4>(p, vec, x, wp, bias, y, s);

@@ -193,3 +193,36 @@ def test_detection_output_batch_wide_top1_pass_same_records():
     want = np.asarray(out).reshape(got.shape)
     assert np.array_equal(got, want)
     assert (got[0, 0, :, 0] >= 0).sum() > n        # the case really produces detections
+
+
+@pytest.mark.parametrize('shape', [
+    # n, hw, cout, k, s, pads_begin, pads_end, act
+    (64, 28, 32, 3, 1, (1, 1), (1, 1), ('relu',)),        # mnist_bn conv2d
+    (3, 28, 32, 5, 1, (0, 0), (0, 0), None),              # mnist conv (5x5, valid)
+    (2, 31, 64, 7, 2, (3, 3), (3, 3), ('clamp', -0.2, 0.4)),
+    (1, 9, 4, 2, 1, (0, 0), (1, 1), None),
+])
+def test_c1_direct_stem_vs_oracle_and_tiled_kernel(shape):
+    """C_in = 1 stems: the direct kernel against the oracle (Convolution.py:57-87) and against the tiled FFMA kernel."""
+    from oracle import ref_ops
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    n, hw, cout, k, s, pb, pe, act = shape
+    rng = np.random.default_rng(abs(hash(shape[:5])) % (1 << 31))
+    x = rng.standard_normal((n, 1, hw, hw)).astype(np.float32)
+    wt = (rng.standard_normal((cout, 1, k, k)) * np.sqrt(2.0 / (k * k))).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, cout, 1, 1))).astype(np.float32)
+    oh = (hw + pb[0] + pe[0] - k) // s + 1
+    want = _act_ref(ref_ops.conv_special(x, wt, (s, s), pb, pe, 'explicit') + b, act)
+
+    def run():
+        return np.asarray(kernels.conv2d(kernels.to_nhwc(kernels.upload(x)), kernels.upload(wt), (s, s), pb, (oh, oh),
+                                         bias=kernels.upload(b), act=act))
+    direct = run()
+    with _env(B200OV_NO_C1_DIRECT='1'):
+        tiled = run()
+    ok, msg = close(direct, want)
+    assert ok, msg
+    ok, msg = close(direct, tiled)
+    assert ok, msg
