@@ -88,6 +88,16 @@ constexpr int W_EPILOGUE0 = 4 * NUM_SETS;                    // warps 8-11 : epi
 constexpr int W_TMA = W_EPILOGUE0 + 4, W_MMA = W_TMA + 1, W_GATE = W_TMA + 2;    // warpgroup 3: 12, 13, 14 (15 idle)
 // register budget per warpgroup (setmaxnreg): 40 + 2 * 136 + 200 = 512 = 4 * 128 (the launch allocation)
 constexpr int REGS_CONTROL = 40, REGS_PRODUCER = 136, REGS_EPILOGUE = 200;
+// mbarrier arrivals of a whole warp set (stage / accumulator released): every thread (1, the default), or one elected lane per
+// warp behind a __syncwarp (32: -DB200OV_F16_ELECTED_ARRIVE).  32 lanes arriving on one mbarrier are 32 serialised shared-memory
+// atomics (ncu counts them as bank conflicts: as many wavefronts per item as the staged variant's loads), but the elected form
+// measured no faster (GoogLeNet 70.4-70.7 k images/s either way, tools/gpu_r2s.sh / gpu_r2z.sh), so the protocol with the
+// longer clean record stays the default.
+#ifdef B200OV_F16_ELECTED_ARRIVE
+constexpr int ARRIVE_DIV = 32;
+#else
+constexpr int ARRIVE_DIV = 1;
+#endif
 constexpr int EPI_BAR_ID = 1;
 constexpr int ID_A0 = 2;                 // named barriers 2 .. 2 + A_SLOTS - 1: A slot written (producer set + MMA warp)
 constexpr float LO_SCALE = 2048.f;     // 2^11
@@ -298,16 +308,16 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_main_full(i), 1);
-      mbar_init(bar_main_empty(i), NUM_EPILOGUE / 32);     // one arrival per warp: 32 lanes arriving on one mbarrier are 32 serialised shared-memory atomics
+      mbar_init(bar_main_empty(i), NUM_EPILOGUE / ARRIVE_DIV);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_cross_full(i), 1);
-      mbar_init(bar_cross_empty(i), NUM_EPILOGUE / 32);
+      mbar_init(bar_cross_empty(i), NUM_EPILOGUE / ARRIVE_DIV);
     }
     if constexpr (POOL) {
       for (int i = 0; i < p.pool_stages; ++i) {
         mbar_init(bar_pool_full(i), 1);
-        mbar_init(bar_pool_empty(i), SET_THREADS / 32);
+        mbar_init(bar_pool_empty(i), SET_THREADS / ARRIVE_DIV);
       }
       prefetch_tensormap(&map_x);
     }
@@ -692,11 +702,9 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         tmem_st_16x256b_x4(tmem_base + ((uint32_t)(32 * q + 16 * g) << 16) + A_COL0 + as * 32, v);
       }
       if constexpr (POOL) {
-        // (after the stores: see issue_loads.)  One arrival per warp, behind a __syncwarp: every lane has issued the stores
-        // that consume its loads.  Per-lane arrivals were 32 serialised atomics on one shared-memory word -- as many conflict
-        // wavefronts per item as the staged variant's loads themselves (ncu, r2r).
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pool_release[which]);
+        // (after the stores: see issue_loads; ARRIVE_DIV above)
+        if constexpr (ARRIVE_DIV == 32) __syncwarp();
+        if (ARRIVE_DIV == 1 || lane == 0) mbar_arrive(pool_release[which]);
       }
       F16_TIMED(2, tmem_st_wait());
       tc_fence_before();
@@ -768,7 +776,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
         }
         tc_fence_before();
         if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_M0 + buf, NUM_EPILOGUE + 32); }
-        else { __syncwarp(); if (lane == 0) mbar_arrive(bar_main_empty(buf)); }
+        else { if constexpr (ARRIVE_DIV == 32) __syncwarp(); if (ARRIVE_DIV == 1 || lane == 0) mbar_arrive(bar_main_empty(buf)); }
         if (warp == W_EPILOGUE0 && lane == 0) F16_STAMP(7, chunkcount);
         ++chunkcount;
       };
@@ -788,7 +796,7 @@ conv_f16x2_kernel(const Params p, const void* __restrict__ x_raw, const float* _
       }
       tc_fence_before();
       if constexpr (DIRECT_EMPTY) { __syncwarp(); named_bar_arrive(ID_X, NUM_EPILOGUE + 32); }
-      else { __syncwarp(); if (lane == 0) mbar_arrive(bar_cross_empty(xb)); }
+      else { if constexpr (ARRIVE_DIV == 32) __syncwarp(); if (ARRIVE_DIV == 1 || lane == 0) mbar_arrive(bar_cross_empty(xb)); }
       promote();
       // activation (None / ReLU / Clamp as one clamp with infinite bounds), staged in shared memory in the
       // 128B-swizzled box layout TMA expects, STG_BLOCKS 32-column blocks per round.  chk turns NaN as soon

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b200ov {
 
@@ -241,39 +242,41 @@ static int launch_cfg(const ConvP& p0, bool vec, const float* x, const float* wp
 // 0.101 ms for 103 MB of output).  Direct form: C_out / 4 consecutive threads own one output pixel (a float4 of channels each,
 // so a warp writes 512 contiguous bytes), the taps come from L1 and the filter from shared memory.  Same FP32 FMA arithmetic
 // class as conv_ffma_kernel (taps accumulated in (ky, kx) order, bias added last).
-constexpr int C1_MAX_TAPS = 49, C1_MAX_COUT = 64;
-__global__ void __launch_bounds__(256) conv_c1_direct_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ wp,
-                                                             const float* __restrict__ bias, float* __restrict__ y) {
+constexpr int C1_MAX_COUT = 64;
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) conv_c1_direct_kernel(ConvP p, FastDiv d_ohow, FastDiv d_ow, const float* __restrict__ x,
+                                                             const float* __restrict__ wp, const float* __restrict__ bias,
+                                                             float* __restrict__ y) {
   B200OV_PDL_SYNC();
-  __shared__ __align__(16) float ws[C1_MAX_TAPS * C1_MAX_COUT];
-  const int taps = p.kh * p.kw, cg = p.cout >> 2;
-  for (int i = threadIdx.x; i < taps * p.cout; i += blockDim.x) ws[i] = __ldg(wp + (long long)(i / p.cout) * p.ldw + (i % p.cout));
-  __syncthreads();
-  const long long total = (long long)p.M * cg;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(idx / cg), c0 = (int)(idx - (long long)m * cg) * 4;
-    const int img = m / p.ohow, r = m - img * p.ohow;
-    const int oy = r / p.ow, ox = r - oy * p.ow;
-    const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
-    const float* xi = x + (long long)img * p.h * p.w * p.x_ld;
+  // thread -> (pixel lane, channel group): the group is fixed per thread (256 % (C_out / 4) == 0), so its KH x KW x 4 filter
+  // values and bias stay in registers; every index is 32-bit (the host checks the sizes)
+  const int cg = p.cout >> 2, c0 = ((int)threadIdx.x % cg) * 4, ppb = 256 / cg;
+  float4 w4[KH * KW];
+#pragma unroll
+  for (int t = 0; t < KH * KW; ++t) w4[t] = __ldg(reinterpret_cast<const float4*>(wp + t * p.ldw + c0));
+  const float4 b4 = bias != nullptr ? make_float4(__ldg(bias + c0), __ldg(bias + c0 + 1), __ldg(bias + c0 + 2), __ldg(bias + c0 + 3))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t m = blockIdx.x * ppb + threadIdx.x / cg; m < (uint32_t)p.M; m += gridDim.x * ppb) {
+    uint32_t img, r, oy, ox;
+    d_ohow.divmod(m, img, r);
+    d_ow.divmod(r, oy, ox);
+    const int iy0 = (int)oy * p.sh - p.pt, ix0 = (int)ox * p.sw - p.pl;
+    const float* xi = x + img * (uint32_t)(p.h * p.w) + iy0 * p.w + ix0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ky = 0; ky < p.kh; ++ky) {
-      const int iy = iy0 + ky;
-      if ((unsigned)iy >= (unsigned)p.h) continue;             // zero padding (Convolution.py:63)
-      for (int kx = 0; kx < p.kw; ++kx) {
-        const int ix = ix0 + kx;
-        if ((unsigned)ix >= (unsigned)p.w) continue;
-        const float v = __ldg(xi + ((long long)iy * p.w + ix) * p.x_ld);
-        const float4 w4 = *reinterpret_cast<const float4*>(ws + (ky * p.kw + kx) * p.cout + c0);
-        acc.x = fmaf(v, w4.x, acc.x); acc.y = fmaf(v, w4.y, acc.y); acc.z = fmaf(v, w4.z, acc.z); acc.w = fmaf(v, w4.w, acc.w);
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+      const bool row_ok = (unsigned)(iy0 + ky) < (unsigned)p.h;
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const bool ok = row_ok && (unsigned)(ix0 + kx) < (unsigned)p.w;       // zero padding (Convolution.py:63)
+        const float v = ok ? __ldg(xi + ky * p.w + kx) : 0.f;
+        const float4 w = w4[ky * KW + kx];
+        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
       }
     }
-    if (bias != nullptr) {
-      acc.x += __ldg(bias + c0); acc.y += __ldg(bias + c0 + 1); acc.z += __ldg(bias + c0 + 2); acc.w += __ldg(bias + c0 + 3);
-    }
-    acc.x = apply_act(acc.x, p.act, p.lo, p.hi); acc.y = apply_act(acc.y, p.act, p.lo, p.hi);
-    acc.z = apply_act(acc.z, p.act, p.lo, p.hi); acc.w = apply_act(acc.w, p.act, p.lo, p.hi);
-    *reinterpret_cast<float4*>(y + (long long)m * p.y_ld + c0) = acc;
+    acc.x = apply_act(acc.x + b4.x, p.act, p.lo, p.hi); acc.y = apply_act(acc.y + b4.y, p.act, p.lo, p.hi);
+    acc.z = apply_act(acc.z + b4.z, p.act, p.lo, p.hi); acc.w = apply_act(acc.w + b4.w, p.act, p.lo, p.hi);
+    *reinterpret_cast<float4*>(y + (size_t)m * p.y_ld + c0) = acc;
   }
 }
 
@@ -291,9 +294,14 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
   p.nb_n = 1;
   if (p.M == 0) return B200OV_OK;
-  if (d->cin == 1 && d->cout % 4 == 0 && d->cout <= C1_MAX_COUT && d->kh * d->kw <= C1_MAX_TAPS && d->y_ld % 4 == 0 && aligned16(y) &&
-      getenv("B200OV_NO_C1_DIRECT") == nullptr) {
-    launch_k(conv_c1_direct_kernel, bw_grid((long long)p.M * (d->cout / 4), 256), 256, 0, s, p, x, wp, bias, y);
+  const int cg1 = d->cout / 4;
+  if (d->cin == 1 && d->x_ld == 1 && d->cout % 4 == 0 && d->cout <= C1_MAX_COUT && (cg1 & (cg1 - 1)) == 0 && d->y_ld % 4 == 0 && aligned16(y) &&
+      aligned16(wp) && (long long)d->n * d->h * d->w < 0x7fffffffLL &&
+      ((d->kh == 3 && d->kw == 3) || (d->kh == 5 && d->kw == 5)) && getenv("B200OV_NO_C1_DIRECT") == nullptr) {
+    const int ppb = 256 / cg1;
+    const int grid = bw_grid((long long)ceil_div(p.M, ppb) * 256, 256);
+    if (d->kh == 3) launch_k(conv_c1_direct_kernel<3, 3>, grid, 256, 0, s, p, FastDiv(p.ohow), FastDiv(d->ow), x, wp, bias, y);
+    else launch_k(conv_c1_direct_kernel<5, 5>, grid, 256, 0, s, p, FastDiv(p.ohow), FastDiv(d->ow), x, wp, bias, y);
     B200OV_LAUNCH_CHECK("conv_c1_direct_kernel");
     return B200OV_OK;
   }

@@ -243,7 +243,10 @@ def test_googlenet_batch256_rows_are_batch1_results(model_dir):
     name, out = net.inputs[0]['name'], net.outputs[0]['name']
     full = exe.infer({name: x})[out]
     assert full.shape == (256, 1000)
-    assert np.array_equal(full, exe.infer({name: x})[out])
+    again = exe.infer({name: x})[out]
+    bad_rows = np.unique(np.nonzero(full != again)[0])
+    assert bad_rows.size == 0, 'replay 1 and replay 2 differ in rows {} (max |d| {:.3g})'.format(
+        bad_rows[:16].tolist(), float(np.abs(full - again).max()))
     assert np.all(np.isfinite(full)) and np.all(full >= 0)
     assert np.allclose(full.sum(axis=1), 1.0, atol=1e-5)
     net1, exe1 = _load(model_dir, 'googlenet-v1', batch=1)
