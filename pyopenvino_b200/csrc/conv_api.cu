@@ -3,6 +3,7 @@
 
 namespace b200ov {
 int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y, cudaStream_t s);
+bool conv2d_c1_direct_ok(const b200ov_conv_desc* d, const void* x, const void* wp, const void* y);
 // tcgen05 path (gemm_tcgen05.cu): returns B200OV_ERR_UNSUPPORTED when the shape is not eligible
 int conv2d_tcgen05(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
                    cudaStream_t s, bool probe_only);
@@ -65,6 +66,10 @@ int b200ov_conv2d(const b200ov_conv_desc* d, const void* x_raw, const float* w_p
       return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: pre_pool needs the f16x2 path on FP32 feature maps");
     return conv2d_f16x2(d, x_raw, f16_section(d, w_packed), bias, y_raw, s);
   }
+  if (d->x_dtype == B200OV_DT_F32 && d->y_dtype == B200OV_DT_HL && d->cin == 1 && (d->math == B200OV_MATH_AUTO || d->math == B200OV_MATH_FP32) &&
+      conv2d_c1_direct_ok(d, x_raw, w_packed, y_raw))
+    // C_in = 1 stem whose only readers are contractions: the direct FP32 kernel writes their (hi, lo) operand form
+    return conv2d_ffma(d, static_cast<const float*>(x_raw), w_packed, bias, static_cast<float*>(y_raw), s);
   if (d->x_dtype != B200OV_DT_F32 || d->y_dtype != B200OV_DT_F32) {
     // FP16 feature maps: only the f16x2 contraction reads / writes them
     B200OV_REQUIRE((d->x_dtype == B200OV_DT_F32 || d->x_dtype == B200OV_DT_F16 || d->x_dtype == B200OV_DT_HL) &&

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f16split.cuh"
 #include "fastdiv.cuh"
 
 namespace b200ov {
@@ -243,7 +244,9 @@ static int launch_cfg(const ConvP& p0, bool vec, const float* x, const float* wp
 // so a warp writes 512 contiguous bytes), the taps come from L1 and the filter from shared memory.  Same FP32 FMA arithmetic
 // class as conv_ffma_kernel (taps accumulated in (ky, kx) order, bias added last).
 constexpr int C1_MAX_COUT = 64;
-template <int KH, int KW>
+// HL: the result is written as the (hi, lo) FP16 pairs the f16x2 contraction that reads it would otherwise compute per tap
+// (B200OV_DT_HL; same bits downstream, see conv_f16x2.cu).
+template <int KH, int KW, bool HL>
 __global__ void __launch_bounds__(256) conv_c1_direct_kernel(ConvP p, FastDiv d_ohow, FastDiv d_ow, const float* __restrict__ x,
                                                              const float* __restrict__ wp, const float* __restrict__ bias,
                                                              float* __restrict__ y) {
@@ -276,8 +279,19 @@ __global__ void __launch_bounds__(256) conv_c1_direct_kernel(ConvP p, FastDiv d_
     }
     acc.x = apply_act(acc.x + b4.x, p.act, p.lo, p.hi); acc.y = apply_act(acc.y + b4.y, p.act, p.lo, p.hi);
     acc.z = apply_act(acc.z + b4.z, p.act, p.lo, p.hi); acc.w = apply_act(acc.w + b4.w, p.act, p.lo, p.hi);
+    if constexpr (HL) acc = encode_hl4(acc.x, acc.y, acc.z, acc.w);
     *reinterpret_cast<float4*>(y + (size_t)m * p.y_ld + c0) = acc;
   }
+}
+
+// shapes the direct C_in = 1 kernel takes (3x3 / 5x5, C_out a multiple of 4 with a power-of-two number of channel groups)
+bool conv2d_c1_direct_ok(const b200ov_conv_desc* d, const void* x, const void* wp, const void* y) {
+  const int cg = d->cout / 4;
+  return d->cin == 1 && d->x_ld == 1 && d->x_dtype == B200OV_DT_F32 && d->cout % 4 == 0 && d->cout <= C1_MAX_COUT && cg > 0 &&
+         (cg & (cg - 1)) == 0 && d->y_ld % 4 == 0 && aligned16(y) && aligned16(wp) && x != nullptr &&
+         (long long)d->n * d->h * d->w < 0x7fffffffLL && ((d->kh == 3 && d->kw == 3) || (d->kh == 5 && d->kw == 5)) &&
+         (d->y_dtype == B200OV_DT_F32 || (d->y_dtype == B200OV_DT_HL && d->act != B200OV_ACT_SIGMOID)) &&
+         getenv("B200OV_NO_C1_DIRECT") == nullptr;
 }
 
 int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
@@ -294,17 +308,19 @@ int conv2d_ffma(const b200ov_conv_desc* d, const float* x, const float* wp, cons
   p.act = d->act; p.lo = d->act_lo; p.hi = d->act_hi;
   p.nb_n = 1;
   if (p.M == 0) return B200OV_OK;
-  const int cg1 = d->cout / 4;
-  if (d->cin == 1 && d->x_ld == 1 && d->cout % 4 == 0 && d->cout <= C1_MAX_COUT && (cg1 & (cg1 - 1)) == 0 && d->y_ld % 4 == 0 && aligned16(y) &&
-      aligned16(wp) && (long long)d->n * d->h * d->w < 0x7fffffffLL &&
-      ((d->kh == 3 && d->kw == 3) || (d->kh == 5 && d->kw == 5)) && getenv("B200OV_NO_C1_DIRECT") == nullptr) {
-    const int ppb = 256 / cg1;
+  if (conv2d_c1_direct_ok(d, x, wp, y)) {
+    const int cg1 = d->cout / 4, ppb = 256 / cg1;
     const int grid = bw_grid((long long)ceil_div(p.M, ppb) * 256, 256);
-    if (d->kh == 3) launch_k(conv_c1_direct_kernel<3, 3>, grid, 256, 0, s, p, FastDiv(p.ohow), FastDiv(d->ow), x, wp, bias, y);
-    else launch_k(conv_c1_direct_kernel<5, 5>, grid, 256, 0, s, p, FastDiv(p.ohow), FastDiv(d->ow), x, wp, bias, y);
+    const bool hl = d->y_dtype == B200OV_DT_HL;
+    const FastDiv d_ohow(p.ohow), d_ow(d->ow);
+    if (d->kh == 3 && hl) launch_k(conv_c1_direct_kernel<3, 3, true>, grid, 256, 0, s, p, d_ohow, d_ow, x, wp, bias, y);
+    else if (d->kh == 3) launch_k(conv_c1_direct_kernel<3, 3, false>, grid, 256, 0, s, p, d_ohow, d_ow, x, wp, bias, y);
+    else if (hl) launch_k(conv_c1_direct_kernel<5, 5, true>, grid, 256, 0, s, p, d_ohow, d_ow, x, wp, bias, y);
+    else launch_k(conv_c1_direct_kernel<5, 5, false>, grid, 256, 0, s, p, d_ohow, d_ow, x, wp, bias, y);
     B200OV_LAUNCH_CHECK("conv_c1_direct_kernel");
     return B200OV_OK;
   }
+  if (d->y_dtype != B200OV_DT_F32) return set_error(B200OV_ERR_UNSUPPORTED, "conv2d: the FP32 FMA kernels write float32 feature maps only");
   const bool vec = (d->cin % 4 == 0) && (d->x_ld % 4 == 0) && aligned16(x);
   const int sms = props().sm_count;
   if (d->cout <= 32) return launch_cfg<128, 32, 4, 4>(p, vec, x, wp, bias, y, s);

@@ -4,6 +4,7 @@ This is the only module that talks to the C ABI for compute.  Nothing here does 
 host; numpy is used to stage host inputs for upload and nothing else.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -304,7 +305,11 @@ def conv2d(x, w, strides, pads_begin, out_hw, bias=None, act=None, out=None, mat
         out = final
     else:
         st = pick_st(pk.cout) if half_ok else 'f32'
-        if hl_out and half_ok and st == 'f32' and final is None and pk.cout % 8 == 0:
+        # C_in = 1 stems run the direct FP32 kernel, which can write the pair form too (conv_ffma.cu: conv2d_c1_direct_ok)
+        c1_hl = (c == 1 and x.st == 'f32' and x.ld == 1 and (pk.kh, pk.kw) in ((3, 3), (5, 5)) and pk.cout <= 64 and
+                 (pk.cout // 4) & (pk.cout // 4 - 1) == 0 and mode == _cabi.MATH_AUTO and code != _cabi.ACT_SIGMOID and
+                 storage == 'f32' and os.environ.get('B200OV_NO_C1_DIRECT') is None)
+        if hl_out and (half_ok or c1_hl) and st == 'f32' and final is None and pk.cout % 8 == 0:
             st = 'hl'
         out = new_nhwc(*shape, st=st)
     d = _cabi.ConvDesc(n=n, h=h, w=wd, cin=c, cout=pk.cout, kh=pk.kh, kw=pk.kw, sh=strides[0], sw=strides[1],

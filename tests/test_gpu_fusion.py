@@ -184,7 +184,7 @@ def test_hl_group_segments(model_dir):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize('model,batch', [('googlenet-v1', 8), ('ssd_mobilenet_v1_coco', 2)])
+@pytest.mark.parametrize('model,batch', [('googlenet-v1', 8), ('ssd_mobilenet_v1_coco', 2), ('mnist_bn', 96)])
 def test_models_with_hl_edges_bit_identical(model_dir, model, batch):
     """Whole networks: the plan with contraction -> contraction tensors in (hi, lo) form against B200OV_NO_HL=1."""
     from pyopenvino_b200.inference_engine import IECore

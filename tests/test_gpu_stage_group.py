@@ -226,3 +226,26 @@ def test_c1_direct_stem_vs_oracle_and_tiled_kernel(shape):
     assert ok, msg
     ok, msg = close(direct, tiled)
     assert ok, msg
+
+
+@pytest.mark.parametrize('k', [3, 5])
+def test_c1_direct_stem_hl_output_feeds_contraction_bit_identically(k):
+    """C_in = 1 stem -> 3x3 convolution: the stem's direct kernel writing the (hi, lo) operand form must give the consumer
+    the same bits as the FP32 edge (the split is the one the consumer's producers would apply)."""
+    from pyopenvino_b200 import kernels
+    from pyopenvino_b200 import device as dev
+    dev.init()
+    rng = np.random.default_rng(k)
+    n, hw, c1, c2 = 6, 28, 32, 64
+    x = rng.standard_normal((n, 1, hw, hw)).astype(np.float32)
+    w1 = (rng.standard_normal((c1, 1, k, k)) * np.sqrt(2.0 / (k * k))).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal((1, c1, 1, 1))).astype(np.float32)
+    w2 = (rng.standard_normal((c2, c1, 3, 3)) * np.sqrt(2.0 / (9 * c1))).astype(np.float32)
+    p = k // 2
+    outs = []
+    for hl in (True, False):
+        y1 = kernels.conv2d(kernels.to_nhwc(kernels.upload(x)), kernels.upload(w1), (1, 1), (p, p), (hw, hw), bias=kernels.upload(b1),
+                            act=('relu',), hl_out=hl)
+        assert y1.st == ('hl' if hl else 'f32')
+        outs.append(np.asarray(kernels.conv2d(y1, kernels.upload(w2), (1, 1), (1, 1), (hw, hw))))
+    assert np.array_equal(outs[0], outs[1])
