@@ -90,9 +90,9 @@ constexpr int W_TMA = W_EPILOGUE0 + 4, W_MMA = W_TMA + 1, W_GATE = W_TMA + 2;   
 constexpr int REGS_CONTROL = 40, REGS_PRODUCER = 136, REGS_EPILOGUE = 200;
 // mbarrier arrivals of a whole warp set (stage / accumulator released): every thread (1, the default), or one elected lane per
 // warp behind a __syncwarp (32: -DB200OV_F16_ELECTED_ARRIVE).  32 lanes arriving on one mbarrier are 32 serialised shared-memory
-// atomics (ncu counts them as bank conflicts: as many wavefronts per item as the staged variant's loads), but the elected form
-// measured no faster (GoogLeNet 70.4-70.7 k images/s either way, tools/gpu_r2s.sh / gpu_r2z.sh), so the protocol with the
-// longer clean record stays the default.
+// atomics, but the elected form measured no faster (GoogLeNet 70.4-70.7 k images/s either way, and ncu's shared-memory
+// bank-conflict count of the staged kernels is the same with both: tools/gpu_r2s.sh, gpu_r2v.sh / gpu_r2bb.sh), so the
+// protocol with the longer clean record stays the default.
 #ifdef B200OV_F16_ELECTED_ARRIVE
 constexpr int ARRIVE_DIV = 32;
 #else
