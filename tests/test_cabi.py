@@ -63,3 +63,19 @@ def test_invalid_descriptor_is_rejected_without_a_gpu(lib_path):
     assert b'conv2d' in lib.b200ov_last_error()
     with pytest.raises(_cabi.B200ovError):
         _cabi.call('b200ov_softmax', None, None, 1, 10, None)
+
+
+def test_round2_entry_points_validate_without_a_gpu(lib_path):
+    """b200ov_concat_rows / b200ov_detection_output_ws (round 2): argument checks and the workspace size are host-side."""
+    from pyopenvino_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.b200ov_concat_rows(0, None, None, None, 1, None) == _cabi.ERR_INVALID
+    assert b'concat_rows' in lib.b200ov_last_error()
+    srcs = (ctypes.c_void_p * 9)(*([None] * 9))
+    cols = (ctypes.c_int * 9)(*([4] * 9))
+    assert lib.b200ov_concat_rows(9, srcs, cols, None, 1, None) == _cabi.ERR_INVALID        # more than B200OV_CONCAT_MAX_PARTS
+    d = _cabi.DetectionDesc(n=64, num_priors=1917, num_classes=91, keep_top_k=100)
+    nbytes = ctypes.c_size_t(0)
+    assert lib.b200ov_detection_output_workspace(ctypes.byref(d), ctypes.byref(nbytes)) == 0
+    assert nbytes.value == 64 * 1917 * 8                      # (score, class) per prior
+    assert lib.b200ov_detection_output_ws(ctypes.byref(d), None, None, None, None, None, 0, None) == _cabi.ERR_INVALID

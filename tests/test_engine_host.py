@@ -190,3 +190,29 @@ def test_no_gpu_fails_loudly():
     from pyopenvino_b200 import _cabi, device
     with pytest.raises(_cabi.B200ovError):
         device.init()
+
+
+def test_operand_form_edge_census(ie, model_dir, monkeypatch):
+    """tensors whose every reader is a contraction are planned in the (hi, lo) operand form -- the *_reduce
+    outputs of GoogLeNet, depthwise -> pointwise and the 1x1 -> 3x3/s2 pairs of SSD, conv -> conv of mnist_bn; none when a
+    MaxPool / Concat / Result reads the tensor, under FP16 storage, or with B200OV_NO_HL=1."""
+    expect = {'mnist': 0, 'mnist_bn': 2, 'googlenet-v1': 19, 'ssd_mobilenet_v1_coco': 22}
+    for model, count in expect.items():
+        path = os.path.join(REPO, 'models', 'mnist.xml') if model == 'mnist' else os.path.join(model_dir, model + '.xml')
+        net = ie.read_network(path, None)
+        exe = ie.load_network(net)
+        plan = exe.build_plan()
+        G = net.G
+        heads = [n for n in exe.task_list if plan[n]['ops'].get('hl_out')]
+        assert len(heads) == count, (model, len(heads))
+        for n in heads:
+            assert G.nodes[n]['type'] in ('Convolution', 'GroupConvolution') and plan[n]['out_slot'] is None
+            for r in G.successors(plan[n]['store_as']):
+                assert G.nodes[r]['type'] == 'Convolution' and 'pre_pool' not in plan[r]['ops']
+    net = ie.read_network(os.path.join(model_dir, 'googlenet-v1.xml'), None)
+    exe = ie.load_network(net, storage='f16')
+    assert not any(st['ops'].get('hl_out') for st in exe.build_plan().values())
+    monkeypatch.setenv('B200OV_NO_HL', '1')
+    net = ie.read_network(os.path.join(model_dir, 'googlenet-v1.xml'), None)
+    exe = ie.load_network(net)
+    assert not any(st['ops'].get('hl_out') for st in exe.build_plan().values())
