@@ -24,6 +24,9 @@
 //   warp 14     gate     : polls the mbarriers the MMA warp depends on (weight stage landed; accumulators drained,
 //                          when the epilogue does not signal the MMA warp directly) and forwards them as arrivals
 //                          on the stage's named barrier.
+//   warp 15     pixel-tile loader (POOL / staged variants only, idle otherwise): one TMA box of the input map per
+//                          slot into a shared-memory ring the A producers read instead of gathering from global
+//                          memory (MaxPool 3x3/s1 folded into a 1x1 convolution; streamed 1x1 inputs).
 //   warps 0-7   A        : im2col gather straight from the NHWC feature map into registers (256-bit loads,
 //                          4 threads cover one pixel's 32-channel run), FP32 -> FP16 hi/lo split (F2FP, FMUL2,
 //                          mixed-precision FHFMA), and tcgen05.st into a TMEM ring of 4 or 8 slots.  Two sets of
@@ -33,7 +36,10 @@
 //   warps 8-11  epilogue : drain the hi*hi accumulator every 256 K-elements into FP32 registers ("promotion",
 //                          see below), add the cross terms, bias, activation, stage the tile in shared memory
 //                          and write it with TMA stores (coalesced, asynchronous), overlapping the next tile.
-// DESIGN.md section 5.1 has the measurements behind each of these choices.
+// Host-side re-descriptions on top of the same kernel: C_in <= 4 stems as 8-channel convolutions over super-pixels, with
+// `group` horizontally adjacent output pixels per GEMM row (conv2d_f16x2_multi); sibling 1x1 convolutions as one GEMM
+// with up to three output tensors; split-K for MatMuls with few tiles.
+// DESIGN.md sections 5.1 - 5.7 have the measurements behind each of these choices.
 //
 // Accuracy engineering (as in gemm_tcgen05.cu): the tensor core truncates when it adds into the FP32
 // accumulator.  The hi*hi accumulator therefore ping-pongs between two TMEM buffers and is added into
